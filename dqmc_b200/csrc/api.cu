@@ -1,0 +1,911 @@
+// C ABI of libdqmc_b200: context, operator ingestion, the propagate state machine of the reference
+// (stack.jl:391-499) driving the CUDA kernels, and the sweep entry points.  See include/dqmc_b200.h.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/dqmc_b200.h"
+#include "blockops.cuh"
+#include "common.cuh"
+#include "local_updates.cuh"
+#include "misc.cuh"
+#include "qr.cuh"
+#include "zgemm.cuh"
+
+char g_errbuf[512] = {0};
+long long g_launches = 0;
+
+enum { F_HBH = 0, F_HA, F_HBH_MU, F_HBHINV, F_HAINV, F_MUINV_HBHINV, F_COUNT };
+enum { TM_WRAP = 0, TM_LOCAL, TM_UDT, TM_GREENS, TM_SWEEP, TM_COUNT };
+
+struct HostCSC {
+  bool set = false;
+  int n = 0;
+  std::vector<int64_t> colptr, rowval;
+  std::vector<cplx> nz;
+};
+
+struct TimerRec { int cat; cudaEvent_t a, b; };
+
+struct dqmc_ctx {
+  dqmc_params p;
+  int n, N, M, sm, nel, kmax;
+  int num_sms;
+  cudaStream_t st;
+  char err[512];
+  // state (1-based like the reference)
+  int current_slice, direction;
+  // device buffers
+  cplx *G, *Gtmp, *u_stack, *t_stack;
+  double* d_stack;
+  cplx *Ul, *Ur, *Tl, *Tr;
+  double *Dl, *Dr;
+  cplx* W[5];
+  cplx *tau, *tfac, *trsm_work;
+  double *dabs, *drp_inv, *colnorm;
+  int* perm;
+  double* hs;
+  double* hs_bak;
+  int* nbr;
+  cplx *At, *Bm;
+  double* unif;
+  long long unif_cap, unif_n;
+  long long* d_pos;
+  long long* d_acc;
+  double* d_dS;
+  int* d_flags;
+  unsigned int* d_bar;
+  double* d_logdet;
+  double* d_check;     // [0] running max, [1] scratch
+  bool have_nbr, ops_ready;
+  HostCSC csc[DQMC_OP_COUNT];
+  QuadOp fop[F_COUNT];
+  int lu_grid, lu_rpc;
+  bool timing;
+  std::vector<TimerRec> trecs;
+  std::vector<cudaEvent_t> evpool;
+  double tacc[TM_COUNT];
+};
+
+#define CTX_FAIL(ctx, ...)                                   \
+  do {                                                       \
+    snprintf(g_errbuf, sizeof(g_errbuf), __VA_ARGS__);       \
+    if (ctx) memcpy((ctx)->err, g_errbuf, sizeof(g_errbuf)); \
+    return -1;                                               \
+  } while (0)
+#define TRY(ctx, expr)                                         \
+  do {                                                         \
+    if ((expr) != 0) {                                         \
+      if (ctx) memcpy((ctx)->err, g_errbuf, sizeof(g_errbuf)); \
+      return -1;                                               \
+    }                                                          \
+  } while (0)
+#define CU(ctx, expr)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) CTX_FAIL(ctx, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static const cplx ONE = {1.0, 0.0}, ZERO = {0.0, 0.0};
+
+// ---------------------------------------------------------------------------------------------- timers
+static cudaEvent_t ev_get(dqmc_ctx* c) {
+  if (!c->evpool.empty()) { cudaEvent_t e = c->evpool.back(); c->evpool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ScopedTimer {
+  dqmc_ctx* c; int cat; cudaEvent_t a;
+  ScopedTimer(dqmc_ctx* c_, int cat_) : c(c_), cat(cat_), a(nullptr) {
+    if (c->timing) { a = ev_get(c); cudaEventRecord(a, c->st); }
+  }
+  ~ScopedTimer() {
+    if (a) { cudaEvent_t b = ev_get(c); cudaEventRecord(b, c->st); c->trecs.push_back({cat, a, b}); }
+  }
+};
+static void timers_resolve(dqmc_ctx* c) {
+  for (auto& r : c->trecs) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    c->tacc[r.cat] += ms;
+    c->evpool.push_back(r.a);
+    c->evpool.push_back(r.b);
+  }
+  c->trecs.clear();
+}
+
+// ---------------------------------------------------------------------------------------------- create / destroy
+template <typename T>
+static int dmalloc(dqmc_ctx* c, T** p, size_t count) {
+  CU(c, cudaMalloc((void**)p, sizeof(T) * count));
+  CU(c, cudaMemsetAsync(*p, 0, sizeof(T) * count, c->st));
+  return 0;
+}
+
+extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
+  if (!out || !p) CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: null argument");
+  if (p->opdim != 3 || p->flv != 4) CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: only the O(3) model (opdim=3, flv=4) is implemented");
+  if (p->slices <= 0 || p->safe_mult <= 0 || p->slices % p->safe_mult != 0)
+    CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: slices must be a positive multiple of safe_mult (stack.jl:189)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: no CUDA device (libdqmc_b200 has no CPU fallback)");
+  if (p->device < 0 || p->device >= ndev) CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: device %d out of range", p->device);
+  dqmc_ctx* c = new dqmc_ctx();
+  memset(c->err, 0, sizeof(c->err));
+  c->p = *p;
+  c->N = p->L * p->L;
+  c->n = p->flv * c->N;
+  c->M = p->slices;
+  c->sm = p->safe_mult;
+  c->nel = c->M / c->sm + 1;
+  c->kmax = p->delay > 0 ? p->delay : 16;
+  if (c->kmax > 32) c->kmax = 32;
+  c->have_nbr = c->ops_ready = false;
+  c->timing = false;
+  for (int i = 0; i < TM_COUNT; ++i) c->tacc[i] = 0.0;
+  c->current_slice = c->M + 1;
+  c->direction = -1;
+  if (c->n % 8 != 0) { delete c; CTX_FAIL((dqmc_ctx*)nullptr, "dqmc_create: n = 4 L^2 must be a multiple of 8"); }
+  CU(c, cudaSetDevice(p->device));
+  cudaDeviceProp prop;
+  CU(c, cudaGetDeviceProperties(&prop, p->device));
+  c->num_sms = prop.multiProcessorCount;
+  CU(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  const size_t n = c->n, nn = n * n;
+  TRY(c, dmalloc(c, &c->G, nn));
+  TRY(c, dmalloc(c, &c->Gtmp, nn));
+  TRY(c, dmalloc(c, &c->u_stack, nn * c->nel));
+  TRY(c, dmalloc(c, &c->t_stack, nn * c->nel));
+  TRY(c, dmalloc(c, &c->d_stack, n * c->nel));
+  TRY(c, dmalloc(c, &c->Ul, nn)); TRY(c, dmalloc(c, &c->Ur, nn));
+  TRY(c, dmalloc(c, &c->Tl, nn)); TRY(c, dmalloc(c, &c->Tr, nn));
+  TRY(c, dmalloc(c, &c->Dl, n)); TRY(c, dmalloc(c, &c->Dr, n));
+  for (int i = 0; i < 5; ++i) TRY(c, dmalloc(c, &c->W[i], nn));
+  TRY(c, dmalloc(c, &c->tau, n));
+  const size_t nblk = (n + QR_NB - 1) / QR_NB;
+  TRY(c, dmalloc(c, &c->tfac, nblk * QR_NB * QR_NB));
+  TRY(c, dmalloc(c, &c->trsm_work, nblk * QR_NB * QR_NB));
+  TRY(c, dmalloc(c, &c->dabs, n)); TRY(c, dmalloc(c, &c->drp_inv, n)); TRY(c, dmalloc(c, &c->colnorm, n));
+  TRY(c, dmalloc(c, &c->perm, n));
+  TRY(c, dmalloc(c, &c->hs, (size_t)3 * c->N * c->M));
+  TRY(c, dmalloc(c, &c->hs_bak, (size_t)3 * c->N * c->M));
+  TRY(c, dmalloc(c, &c->nbr, (size_t)4 * c->N));
+  TRY(c, dmalloc(c, &c->At, (size_t)4 * c->kmax * n));
+  TRY(c, dmalloc(c, &c->Bm, (size_t)4 * c->kmax * n));
+  c->unif = nullptr; c->unif_cap = c->unif_n = 0;
+  TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
+  TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
+  TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
+  for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
+  c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
+  CU(c, cudaStreamSynchronize(c->st));
+  *out = c;
+  return 0;
+}
+
+extern "C" int dqmc_destroy(dqmc_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->p.device);
+  cudaStreamSynchronize(c->st);
+  timers_resolve(c);
+  for (auto e : c->evpool) cudaEventDestroy(e);
+  void* ptrs[] = {c->G, c->Gtmp, c->u_stack, c->t_stack, c->d_stack, c->Ul, c->Ur, c->Tl, c->Tr, c->Dl, c->Dr,
+                  c->W[0], c->W[1], c->W[2], c->W[3], c->W[4], c->tau, c->tfac, c->trsm_work, c->dabs, c->drp_inv,
+                  c->colnorm, c->perm, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
+                  c->d_flags, c->d_bar, c->d_logdet, c->d_check};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < F_COUNT; ++i) { if (c->fop[i].idx) cudaFree(c->fop[i].idx); if (c->fop[i].val) cudaFree(c->fop[i].val); }
+  cudaStreamDestroy(c->st);
+  delete c;
+  return 0;
+}
+
+extern "C" const char* dqmc_last_error(dqmc_ctx* c) { return c ? c->err : g_errbuf; }
+extern "C" int64_t dqmc_kernel_launches(dqmc_ctx*) { return g_launches; }
+
+// ---------------------------------------------------------------------------------------------- operators
+struct HostQuad { std::vector<int> idx; std::vector<cplx> val; };
+
+static int find_root(std::vector<int>& par, int x) {
+  while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
+  return x;
+}
+
+// CSC -> disjoint index groups (connected components of the sparsity pattern) packed into 4-index blocks.
+static int csc_to_quad(dqmc_ctx* c, const HostCSC& m, HostQuad* q) {
+  const int n = m.n;
+  std::vector<int> par(n);
+  std::iota(par.begin(), par.end(), 0);
+  for (int j = 0; j < n; ++j)
+    for (int64_t k = m.colptr[j] - 1; k < m.colptr[j + 1] - 1; ++k) {
+      int r = (int)m.rowval[k] - 1;
+      int a = find_root(par, r), b = find_root(par, j);
+      if (a != b) par[a] = b;
+    }
+  std::vector<std::vector<int>> comp(n);
+  for (int i = 0; i < n; ++i) comp[find_root(par, i)].push_back(i);
+  std::vector<std::vector<int>> by_size[5];
+  for (int i = 0; i < n; ++i) {
+    if (comp[i].empty()) continue;
+    if (comp[i].size() > 4)
+      CTX_FAIL(c, "operator couples %zu indices in one group; only checkerboard factors made of <=4-site blocks are "
+                  "supported (folded CBGeneric groups are out of scope)", comp[i].size());
+    by_size[comp[i].size()].push_back(comp[i]);
+  }
+  std::vector<std::vector<int>> blocks = by_size[4];
+  auto merge = [&](std::vector<std::vector<int>>& src, size_t per) -> int {
+    if (src.size() % per) return -1;
+    for (size_t i = 0; i < src.size(); i += per) {
+      std::vector<int> b;
+      for (size_t k = 0; k < per; ++k) b.insert(b.end(), src[i + k].begin(), src[i + k].end());
+      blocks.push_back(b);
+    }
+    return 0;
+  };
+  // 3+1, then 2+2, then 1+1+1+1
+  while (!by_size[3].empty() && !by_size[1].empty()) {
+    std::vector<int> b = by_size[3].back(); by_size[3].pop_back();
+    b.push_back(by_size[1].back()[0]); by_size[1].pop_back();
+    blocks.push_back(b);
+  }
+  if (!by_size[3].empty()) CTX_FAIL(c, "operator block structure cannot be packed into 4-index blocks");
+  if (by_size[2].size() % 2 == 1 && by_size[1].size() >= 2) {
+    std::vector<int> b = by_size[2].back(); by_size[2].pop_back();
+    b.push_back(by_size[1].back()[0]); by_size[1].pop_back();
+    b.push_back(by_size[1].back()[0]); by_size[1].pop_back();
+    blocks.push_back(b);
+  }
+  if (merge(by_size[2], 2) || merge(by_size[1], 4)) CTX_FAIL(c, "operator block structure cannot be packed into 4-index blocks");
+  const int nblk = (int)blocks.size();
+  q->idx.assign((size_t)4 * nblk, 0);
+  q->val.assign((size_t)16 * nblk, ZERO);
+  std::vector<int> where(n), slot(n);
+  for (int b = 0; b < nblk; ++b) {
+    std::sort(blocks[b].begin(), blocks[b].end());
+    for (int k = 0; k < 4; ++k) { q->idx[4 * b + k] = blocks[b][k]; where[blocks[b][k]] = b; slot[blocks[b][k]] = k; }
+  }
+  for (int j = 0; j < n; ++j)
+    for (int64_t k = m.colptr[j] - 1; k < m.colptr[j + 1] - 1; ++k) {
+      int r = (int)m.rowval[k] - 1;
+      q->val[(size_t)16 * where[r] + 4 * slot[r] + slot[j]] = m.nz[k];
+    }
+  return 0;
+}
+
+static int upload_quad(dqmc_ctx* c, const HostQuad& q, QuadOp* d) {
+  if (d->idx) cudaFree(d->idx);
+  if (d->val) cudaFree(d->val);
+  d->nblk = (int)(q.idx.size() / 4);
+  CU(c, cudaMalloc((void**)&d->idx, sizeof(int) * q.idx.size()));
+  CU(c, cudaMalloc((void**)&d->val, sizeof(cplx) * q.val.size()));
+  CU(c, cudaMemcpy(d->idx, q.idx.data(), sizeof(int) * q.idx.size(), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(d->val, q.val.data(), sizeof(cplx) * q.val.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int csc_diag(dqmc_ctx* c, const HostCSC& m, std::vector<cplx>* d) {
+  d->assign(m.n, ZERO);
+  for (int j = 0; j < m.n; ++j)
+    for (int64_t k = m.colptr[j] - 1; k < m.colptr[j + 1] - 1; ++k) {
+      if ((int)m.rowval[k] - 1 != j) CTX_FAIL(c, "chkr_mu operator must be diagonal");
+      (*d)[j] = m.nz[k];
+    }
+  return 0;
+}
+
+static int finalize_operators(dqmc_ctx* c) {
+  for (int i = 0; i < DQMC_OP_COUNT; ++i) if (!c->csc[i].set) return 0;   // wait until all six are there
+  HostQuad hbh, ha, hbhinv, hainv;
+  TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_B], &hbh));
+  TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_A], &ha));
+  TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_INV_B], &hbhinv));
+  TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_INV_A], &hainv));
+  std::vector<cplx> mu, muinv;
+  TRY(c, csc_diag(c, c->csc[DQMC_OP_MU], &mu));
+  TRY(c, csc_diag(c, c->csc[DQMC_OP_MU_INV], &muinv));
+  // fold the diagonal chemical-potential factor into the neighbouring hopping factor:
+  //   B = hBh * hA * (hBh * mu) * e^{-dtau V},   B^-1 = e^{+dtau V} * (mu^-1 * hBh^-1) * hA^-1 * hBh^-1
+  HostQuad hbh_mu = hbh, muinv_hbhinv = hbhinv;
+  for (size_t b = 0; b < hbh.idx.size() / 4; ++b)
+    for (int r = 0; r < 4; ++r)
+      for (int cc = 0; cc < 4; ++cc) hbh_mu.val[16 * b + 4 * r + cc] = cmul(hbh.val[16 * b + 4 * r + cc], mu[hbh.idx[4 * b + cc]]);
+  for (size_t b = 0; b < hbhinv.idx.size() / 4; ++b)
+    for (int r = 0; r < 4; ++r)
+      for (int cc = 0; cc < 4; ++cc)
+        muinv_hbhinv.val[16 * b + 4 * r + cc] = cmul(muinv[hbhinv.idx[4 * b + r]], hbhinv.val[16 * b + 4 * r + cc]);
+  TRY(c, upload_quad(c, hbh, &c->fop[F_HBH]));
+  TRY(c, upload_quad(c, ha, &c->fop[F_HA]));
+  TRY(c, upload_quad(c, hbh_mu, &c->fop[F_HBH_MU]));
+  TRY(c, upload_quad(c, hbhinv, &c->fop[F_HBHINV]));
+  TRY(c, upload_quad(c, hainv, &c->fop[F_HAINV]));
+  TRY(c, upload_quad(c, muinv_hbhinv, &c->fop[F_MUINV_HBHINV]));
+  c->ops_ready = true;
+  return 0;
+}
+
+extern "C" int dqmc_set_operator(dqmc_ctx* c, int which, int64_t m, int64_t n, const int64_t* colptr,
+                                 const int64_t* rowval, const void* nzval, int nz_is_complex) {
+  if (!c) return -1;
+  if (which < 0 || which >= DQMC_OP_COUNT) CTX_FAIL(c, "dqmc_set_operator: unknown operator %d", which);
+  if (m != c->n || n != c->n) CTX_FAIL(c, "dqmc_set_operator: operator is %lldx%lld, expected %dx%d", (long long)m, (long long)n, c->n, c->n);
+  HostCSC& h = c->csc[which];
+  h.n = c->n;
+  h.colptr.assign(colptr, colptr + n + 1);
+  const int64_t nnz = colptr[n] - 1;
+  h.rowval.assign(rowval, rowval + nnz);
+  h.nz.resize(nnz);
+  for (int64_t k = 0; k < nnz; ++k)
+    h.nz[k] = nz_is_complex ? ((const cplx*)nzval)[k] : cmake(((const double*)nzval)[k], 0.0);
+  h.set = true;
+  c->ops_ready = false;
+  CU(c, cudaSetDevice(c->p.device));
+  return finalize_operators(c);
+}
+
+extern "C" int dqmc_set_neighbors(dqmc_ctx* c, const int64_t* neighbors) {
+  if (!c) return -1;
+  std::vector<int> nb((size_t)4 * c->N);
+  for (size_t i = 0; i < nb.size(); ++i) {
+    if (neighbors[i] < 1 || neighbors[i] > c->N) CTX_FAIL(c, "dqmc_set_neighbors: index out of range");
+    nb[i] = (int)neighbors[i] - 1;
+  }
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpy(c->nbr, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice));
+  c->have_nbr = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- simple get/set
+#define NEED_OPS(c) do { if (!(c)->ops_ready) CTX_FAIL(c, "operators not set (dqmc_set_operator for all six factors)"); } while (0)
+
+extern "C" int dqmc_set_hsfield(dqmc_ctx* c, const double* h) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpyAsync(c->hs, h, sizeof(double) * 3 * c->N * c->M, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int dqmc_get_hsfield(dqmc_ctx* c, double* h) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpyAsync(h, c->hs, sizeof(double) * 3 * c->N * c->M, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int dqmc_set_greens(dqmc_ctx* c, const double* g) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpyAsync(c->G, g, sizeof(cplx) * c->n * c->n, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int dqmc_get_greens(dqmc_ctx* c, double* g) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpyAsync(g, c->G, sizeof(cplx) * c->n * c->n, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int dqmc_get_state(dqmc_ctx* c, int32_t* slice, int32_t* direction) {
+  if (slice) *slice = c->current_slice;
+  if (direction) *direction = c->direction;
+  return 0;
+}
+extern "C" int dqmc_set_state(dqmc_ctx* c, int32_t slice, int32_t direction) {
+  if (slice < 0 || slice > c->M + 1 || (direction != 1 && direction != -1)) CTX_FAIL(c, "dqmc_set_state: bad state");
+  c->current_slice = slice;
+  c->direction = direction;
+  return 0;
+}
+extern "C" int dqmc_sync(dqmc_ctx* c) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- B chains
+static void push_op(Chain& ch, const QuadOp& op, int mode) {
+  ChainStep& s = ch.s[ch.nsteps++];
+  s.kind = 0; s.mode = mode; s.nblk = op.nblk; s.slice = 0; s.sign = 0.0; s.idx = op.idx; s.val = op.val;
+}
+static void push_ev(Chain& ch, int slice0, double sign, int mode) {
+  ChainStep& s = ch.s[ch.nsteps++];
+  s.kind = 1; s.mode = mode; s.nblk = 0; s.slice = slice0; s.sign = sign; s.idx = nullptr; s.val = nullptr;
+}
+// append the steps of one multiply_B_* (slice_matrices.jl:101-226); slice 1-based
+static void push_B(dqmc_ctx* c, Chain& ch, int op, int slice) {
+  const int s0 = slice - 1;
+  switch (op) {
+    case DQMC_B_LEFT:         // M <- hBh hA hBh mu eV M
+      push_ev(ch, s0, 1.0, OP_N); push_op(ch, c->fop[F_HBH_MU], OP_N); push_op(ch, c->fop[F_HA], OP_N); push_op(ch, c->fop[F_HBH], OP_N);
+      break;
+    case DQMC_B_INV_LEFT:     // M <- eV^-1 mu^-1 hBh^-1 hA^-1 hBh^-1 M
+      push_op(ch, c->fop[F_HBHINV], OP_N); push_op(ch, c->fop[F_HAINV], OP_N); push_op(ch, c->fop[F_MUINV_HBHINV], OP_N); push_ev(ch, s0, -1.0, OP_N);
+      break;
+    case DQMC_B_DAGGER_LEFT:  // M <- eV mu hBh^† hA^† hBh^† M
+      push_op(ch, c->fop[F_HBH], OP_C); push_op(ch, c->fop[F_HA], OP_C); push_op(ch, c->fop[F_HBH_MU], OP_C); push_ev(ch, s0, 1.0, OP_C);
+      break;
+    case DQMC_B_RIGHT:        // M <- M hBh hA hBh mu eV   (row vector x -> F^T x)
+      push_op(ch, c->fop[F_HBH], OP_T); push_op(ch, c->fop[F_HA], OP_T); push_op(ch, c->fop[F_HBH_MU], OP_T); push_ev(ch, s0, 1.0, OP_T);
+      break;
+    case DQMC_B_INV_RIGHT:    // M <- M eV^-1 mu^-1 hBh^-1 hA^-1 hBh^-1
+      push_ev(ch, s0, -1.0, OP_T); push_op(ch, c->fop[F_MUINV_HBHINV], OP_T); push_op(ch, c->fop[F_HAINV], OP_T); push_op(ch, c->fop[F_HBHINV], OP_T);
+      break;
+  }
+}
+static bool op_is_rows(int op) { return op == DQMC_B_RIGHT || op == DQMC_B_INV_RIGHT; }
+
+static int run_chain(dqmc_ctx* c, bool rows, cplx* mat, const Chain& ch, const double* colscale, double* colnorm2) {
+  return launch_apply_chain(rows, mat, c->n, c->n, ch, c->hs, c->N, c->p.lambda * c->p.delta_tau, colscale, colnorm2,
+                            c->num_sms, c->st);
+}
+
+static int apply_B(dqmc_ctx* c, int op, int slice, cplx* mat) {
+  Chain ch; ch.nsteps = 0;
+  push_B(c, ch, op, slice);
+  return run_chain(c, op_is_rows(op), mat, ch, nullptr, nullptr);
+}
+
+// wrap_greens! (stack.jl:316-325)
+static int wrap_greens_dev(dqmc_ctx* c, cplx* g, int slice, int dir) {
+  ScopedTimer t(c, TM_WRAP);
+  if (dir == -1) {
+    TRY(c, apply_B(c, DQMC_B_INV_LEFT, slice - 1, g));
+    TRY(c, apply_B(c, DQMC_B_RIGHT, slice - 1, g));
+  } else {
+    TRY(c, apply_B(c, DQMC_B_LEFT, slice, g));
+    TRY(c, apply_B(c, DQMC_B_INV_RIGHT, slice, g));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- UDT / greens
+// decompose_udt! (linalg.jl:20-39): X (in c->W[0], destroyed; column norms^2 in c->colnorm) -> U, D, T(W[2]).
+// Pivoting = one stable sort of the columns by norm, then unpivoted blocked Householder QR.
+static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
+  const int n = c->n;
+  TRY(c, argsort_desc(c->st, c->colnorm, n, c->perm));
+  TRY(c, gather_cols(c->st, c->W[0], n, n, c->perm, c->W[1], n, c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, nullptr, 0, 0, c->num_sms));
+  TRY(c, qr_form_q(c->st, c->W[1], n, n, c->tfac, Uout, n, c->num_sms));
+  TRY(c, build_T(c->st, c->W[1], n, n, Dout, c->perm, c->W[2], n, c->num_sms));
+  return 0;
+}
+
+static cplx* uslab(dqmc_ctx* c, int idx1) { return c->u_stack + (size_t)(idx1 - 1) * c->n * c->n; }
+static cplx* tslab(dqmc_ctx* c, int idx1) { return c->t_stack + (size_t)(idx1 - 1) * c->n * c->n; }
+static double* dslab(dqmc_ctx* c, int idx1) { return c->d_stack + (size_t)(idx1 - 1) * c->n; }
+
+// add_slice_sequence_left / _right (stack.jl:278-313); idx 1-based.
+static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
+  ScopedTimer t(c, TM_UDT);
+  const int n = c->n;
+  const size_t nn = (size_t)n * n;
+  const int src = left ? idx : idx + 1, dst = left ? idx + 1 : idx;
+  CU(c, cudaMemcpyAsync(c->W[0], uslab(c, src), sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+  const int lo = 1 + (idx - 1) * c->sm, hi = idx * c->sm;       // s.ranges[idx]
+  Chain ch; ch.nsteps = 0;
+  for (int k = 0; k < c->sm; ++k) {
+    const int slice = left ? lo + k : hi - k;
+    const bool last = (k == c->sm - 1);
+    push_B(c, ch, left ? DQMC_B_LEFT : DQMC_B_DAGGER_LEFT, slice);
+    if (last || ch.nsteps + 4 > DQMC_MAX_CHAIN) {
+      TRY(c, run_chain(c, false, c->W[0], ch, last ? dslab(c, src) : nullptr, last ? c->colnorm : nullptr));
+      ch.nsteps = 0;
+    }
+  }
+  TRY(c, udt_dev(c, uslab(c, dst), dslab(c, dst)));
+  TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[2], n, tslab(c, src), n, ZERO, tslab(c, dst), n, c->num_sms));
+  return 0;
+}
+
+// calculate_greens (stack.jl:338-369): G = [1 + Ul Dl Tl (Ur Dr Tr)^†]^-1, evaluated as
+//   G = Ur Drp^-1 [ Dlp^-1 Ul^† Ur Drp^-1 + Dlm Tl Tr^† Drm ]^-1 Dlp^-1 Ul^†      (Dp = max(D,1), Dm = min(D,1))
+// with one Householder QR of the bracket (Q^† applied to the right-hand side on the fly) and a triangular solve.
+static int calculate_greens_dev(dqmc_ctx* c) {
+  ScopedTimer t(c, TM_GREENS);
+  const int n = c->n;
+  TRY(c, zgemm(c->st, OP_C, OP_N, n, n, n, ONE, c->Ul, n, c->Ur, n, ZERO, c->W[0], n, c->num_sms));
+  TRY(c, zgemm(c->st, OP_N, OP_C, n, n, n, ONE, c->Tl, n, c->Tr, n, ZERO, c->W[1], n, c->num_sms));
+  TRY(c, loh_assemble(c->st, n, c->W[0], c->W[1], c->Dl, c->Dr, c->Ul, c->W[2], c->W[3], c->drp_inv, c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[2], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms));
+  TRY(c, trsm_upper(c->st, c->W[2], n, n, c->W[3], n, n, c->trsm_work, c->drp_inv, c->num_sms));
+  TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
+  return 0;
+}
+
+static int calculate_logdet_dev(dqmc_ctx* c) {
+  return logdet_from_factors(c->st, c->n, c->Dl, c->Dr, c->dabs, c->d_logdet);
+}
+
+static int load_udt(dqmc_ctx* c, int idx1, cplx* U, double* D, cplx* T) {
+  const size_t nn = (size_t)c->n * c->n;
+  CU(c, cudaMemcpyAsync(U, uslab(c, idx1), sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+  CU(c, cudaMemcpyAsync(D, dslab(c, idx1), sizeof(double) * c->n, cudaMemcpyDeviceToDevice, c->st));
+  CU(c, cudaMemcpyAsync(T, tslab(c, idx1), sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+static int set_udt_identity(dqmc_ctx* c, cplx* U, double* D, cplx* T) {
+  TRY(c, set_identity(c->st, U, c->n, c->n, c->num_sms));
+  TRY(c, fill_ones(c->st, D, c->n));
+  TRY(c, set_identity(c->st, T, c->n, c->n, c->num_sms));
+  return 0;
+}
+
+static int check_begin(dqmc_ctx* c) {   // copyto!(s.greens_temp, s.greens)
+  if (!c->p.all_checks) return 0;
+  CU(c, cudaMemcpyAsync(c->Gtmp, c->G, sizeof(cplx) * c->n * c->n, cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+__global__ void check_accumulate_kernel(double* chk) { if (chk[1] > chk[0]) chk[0] = chk[1]; }
+static int check_end(dqmc_ctx* c) {     // maximum(absdiff(s.greens_temp, s.greens))
+  if (!c->p.all_checks) return 0;
+  TRY(c, max_abs_diff(c->st, c->Gtmp, c->G, (size_t)c->n * c->n, c->d_check + 1, c->num_sms));
+  check_accumulate_kernel<<<1, 1, 0, c->st>>>(c->d_check);
+  g_launches++;
+  return 0;
+}
+
+extern "C" int dqmc_build_stack(dqmc_ctx* c) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  TRY(c, set_udt_identity(c, uslab(c, 1), dslab(c, 1), tslab(c, 1)));
+  for (int i = 1; i <= c->nel - 1; ++i) TRY(c, add_slice_sequence(c, i, true));
+  c->current_slice = c->M + 1;
+  c->direction = -1;
+  return 0;
+}
+
+// propagate (stack.jl:391-499); everything is enqueued on the context's stream, nothing synchronises.
+static int propagate_dev(dqmc_ctx* c) {
+  const int M = c->M, sm = c->sm;
+  if (c->direction == 1) {
+    if (c->current_slice % sm == 0) {
+      c->current_slice += 1;
+      if (c->current_slice == 1) {
+        TRY(c, load_udt(c, 1, c->Ur, c->Dr, c->Tr));
+        TRY(c, set_udt_identity(c, uslab(c, 1), dslab(c, 1), tslab(c, 1)));
+        TRY(c, set_udt_identity(c, c->Ul, c->Dl, c->Tl));
+        TRY(c, calculate_greens_dev(c));
+        TRY(c, calculate_logdet_dev(c));
+      } else if (c->current_slice <= M) {
+        const int idx = (c->current_slice - 1) / sm;
+        TRY(c, load_udt(c, idx + 1, c->Ur, c->Dr, c->Tr));
+        TRY(c, add_slice_sequence(c, idx, true));
+        TRY(c, load_udt(c, idx + 1, c->Ul, c->Dl, c->Tl));
+        if (c->p.all_checks) {
+          TRY(c, check_begin(c));
+          TRY(c, wrap_greens_dev(c, c->Gtmp, c->current_slice - 1, 1));
+        }
+        TRY(c, calculate_greens_dev(c));
+        TRY(c, check_end(c));
+      } else {
+        TRY(c, add_slice_sequence(c, c->nel - 1, true));
+        c->direction = -1;
+        c->current_slice = M + 1;
+        return propagate_dev(c);
+      }
+    } else {
+      TRY(c, wrap_greens_dev(c, c->G, c->current_slice, 1));
+      c->current_slice += 1;
+    }
+  } else {
+    if ((c->current_slice - 1) % sm == 0) {
+      c->current_slice -= 1;
+      if (c->current_slice == M) {
+        TRY(c, load_udt(c, c->nel, c->Ul, c->Dl, c->Tl));
+        TRY(c, set_udt_identity(c, uslab(c, c->nel), dslab(c, c->nel), tslab(c, c->nel)));
+        TRY(c, set_udt_identity(c, c->Ur, c->Dr, c->Tr));
+        TRY(c, calculate_greens_dev(c));
+        TRY(c, calculate_logdet_dev(c));
+        TRY(c, wrap_greens_dev(c, c->G, c->current_slice + 1, -1));
+      } else if (c->current_slice > 0) {
+        const int idx = c->current_slice / sm + 1;
+        TRY(c, load_udt(c, idx, c->Ul, c->Dl, c->Tl));
+        TRY(c, add_slice_sequence(c, idx, false));
+        TRY(c, load_udt(c, idx, c->Ur, c->Dr, c->Tr));
+        TRY(c, check_begin(c));
+        TRY(c, calculate_greens_dev(c));
+        TRY(c, check_end(c));
+        TRY(c, wrap_greens_dev(c, c->G, c->current_slice + 1, -1));
+      } else {
+        TRY(c, add_slice_sequence(c, 1, false));
+        c->direction = 1;
+        c->current_slice = 0;
+        return propagate_dev(c);
+      }
+    } else {
+      TRY(c, wrap_greens_dev(c, c->G, c->current_slice, -1));
+      c->current_slice -= 1;
+    }
+  }
+  return 0;
+}
+
+extern "C" int dqmc_propagate(dqmc_ctx* c, int32_t* slice, int32_t* direction) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  TRY(c, propagate_dev(c));
+  if (slice) *slice = c->current_slice;
+  if (direction) *direction = c->direction;
+  return 0;
+}
+
+extern "C" int dqmc_wrap_greens(dqmc_ctx* c, double* g, int32_t slice, int32_t direction) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  const size_t bytes = sizeof(cplx) * c->n * c->n;
+  if (!g) { TRY(c, wrap_greens_dev(c, c->G, slice, direction)); return 0; }
+  CU(c, cudaMemcpyAsync(c->W[4], g, bytes, cudaMemcpyHostToDevice, c->st));
+  TRY(c, wrap_greens_dev(c, c->W[4], slice, direction));
+  CU(c, cudaMemcpyAsync(g, c->W[4], bytes, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_multiply_B(dqmc_ctx* c, int op, int32_t slice, double* m) {
+  NEED_OPS(c);
+  if (op < 0 || op > DQMC_B_DAGGER_LEFT) CTX_FAIL(c, "dqmc_multiply_B: bad op %d", op);
+  if (slice < 1 || slice > c->M) CTX_FAIL(c, "dqmc_multiply_B: slice %d out of range", slice);
+  CU(c, cudaSetDevice(c->p.device));
+  const size_t bytes = sizeof(cplx) * c->n * c->n;
+  CU(c, cudaMemcpyAsync(c->W[4], m, bytes, cudaMemcpyHostToDevice, c->st));
+  TRY(c, apply_B(c, op, slice, c->W[4]));
+  CU(c, cudaMemcpyAsync(m, c->W[4], bytes, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_calculate_greens_from(dqmc_ctx* c, const double* Ul, const double* Dl, const double* Tl,
+                                          const double* Ur, const double* Dr, const double* Tr, double* g) {
+  CU(c, cudaSetDevice(c->p.device));
+  const size_t nn = sizeof(cplx) * c->n * c->n, nd = sizeof(double) * c->n;
+  CU(c, cudaMemcpyAsync(c->Ul, Ul, nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Dl, Dl, nd, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Tl, Tl, nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Ur, Ur, nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Dr, Dr, nd, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Tr, Tr, nn, cudaMemcpyHostToDevice, c->st));
+  TRY(c, calculate_greens_dev(c));
+  TRY(c, calculate_logdet_dev(c));
+  if (g) CU(c, cudaMemcpyAsync(g, c->G, nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_logdet(dqmc_ctx* c, double* logdet) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaMemcpyAsync(logdet, c->d_logdet, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_decompose_udt(dqmc_ctx* c, const double* x, double* U, double* D, double* T) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int n = c->n;
+  const size_t nn = sizeof(cplx) * n * n;
+  CU(c, cudaMemcpyAsync(c->W[0], x, nn, cudaMemcpyHostToDevice, c->st));
+  TRY(c, colnorm2(c->st, c->W[0], n, n, c->colnorm));
+  TRY(c, udt_dev(c, c->W[3], c->dabs));
+  CU(c, cudaMemcpyAsync(U, c->W[3], nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(D, c->dabs, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(T, c->W[2], nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- local updates / sweep
+static int upload_uniforms(dqmc_ctx* c, const double* u, int64_t nu) {
+  if (nu > c->unif_cap) {
+    if (c->unif) cudaFree(c->unif);
+    CU(c, cudaMalloc((void**)&c->unif, sizeof(double) * (size_t)nu));
+    c->unif_cap = nu;
+  }
+  CU(c, cudaMemcpyAsync(c->unif, u, sizeof(double) * (size_t)nu, cudaMemcpyHostToDevice, c->st));
+  c->unif_n = nu;
+  CU(c, cudaMemsetAsync(c->d_pos, 0, sizeof(long long), c->st));
+  return 0;
+}
+
+extern "C" int dqmc_set_uniforms(dqmc_ctx* c, const double* u, int64_t nu) {
+  CU(c, cudaSetDevice(c->p.device));
+  TRY(c, upload_uniforms(c, u, nu));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+static int local_updates_dev(dqmc_ctx* c, double box) {
+  ScopedTimer t(c, TM_LOCAL);
+  if (!c->have_nbr) CTX_FAIL(c, "neighbour table not set (dqmc_set_neighbors)");
+  if (c->current_slice < 1 || c->current_slice > c->M) CTX_FAIL(c, "local_updates: current_slice %d is not a physical slice", c->current_slice);
+  LUArgs a;
+  a.n = c->n; a.nsites = c->N; a.nslices = c->M; a.slice = c->current_slice - 1;
+  a.kmax = c->kmax; a.rpc = c->lu_rpc; a.edrun = c->p.edrun;
+  a.box = box; a.dtau = c->p.delta_tau; a.lam_dtau = c->p.lambda * c->p.delta_tau;
+  a.inv_dtau_c2 = 1.0 / (c->p.delta_tau * c->p.c * c->p.c); a.r = c->p.r; a.u = c->p.u;
+  a.G = c->G; a.At = c->At; a.Bm = c->Bm; a.hs = c->hs; a.nbr = c->nbr;
+  a.unif = c->unif; a.nunif = c->unif_n; a.pos = c->d_pos; a.accepted = c->d_acc; a.dS = c->d_dS;
+  a.flags = c->d_flags; a.bar = c->d_bar;
+  TRY(c, launch_local_updates(c->st, a, c->lu_grid));
+  return 0;
+}
+
+static int counters_reset(dqmc_ctx* c) {
+  CU(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long), c->st));
+  CU(c, cudaMemsetAsync(c->d_dS, 0, sizeof(double), c->st));
+  CU(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->st));   // keep [1] (non-real counter) running
+  return 0;
+}
+static int counters_read(dqmc_ctx* c, int64_t* consumed, int64_t* accepted, double* dS) {
+  long long pos = 0, acc = 0; double ds = 0.0; int flags[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(&pos, c->d_pos, sizeof(pos), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(&acc, c->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(&ds, c->d_dS, sizeof(ds), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  if (consumed) *consumed = pos;
+  if (accepted) *accepted = acc;
+  if (dS) *dS = ds;
+  if (flags[0]) CTX_FAIL(c, "uniform stream exhausted: supply at least 4*N draws per slice");
+  return 0;
+}
+
+extern "C" int dqmc_local_updates(dqmc_ctx* c, double box, const double* u, int64_t nu, int64_t* consumed,
+                                  int64_t* accepted, double* dS_total) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  if (u) TRY(c, upload_uniforms(c, u, nu));
+  TRY(c, counters_reset(c));
+  TRY(c, local_updates_dev(c, box));
+  return counters_read(c, consumed, accepted, dS_total);
+}
+
+extern "C" int dqmc_sweep(dqmc_ctx* c, int32_t nupdates, double box, const double* u, int64_t nu, int64_t* consumed,
+                          int64_t* accepted, double* dS_total) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  if (u) TRY(c, upload_uniforms(c, u, nu));
+  TRY(c, counters_reset(c));
+  {
+    ScopedTimer t(c, TM_SWEEP);
+    for (int k = 0; k < nupdates; ++k) {
+      TRY(c, propagate_dev(c));
+      TRY(c, local_updates_dev(c, box));
+    }
+  }
+  return counters_read(c, consumed, accepted, dS_total);
+}
+
+extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaStreamSynchronize(c->st));
+  timers_resolve(c);
+  for (int i = 0; i < n; ++i) ms[i] = i < TM_COUNT ? c->tacc[i] : 0.0;
+  for (int i = 0; i < TM_COUNT; ++i) c->tacc[i] = 0.0;
+  return 0;
+}
+
+extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t enable) {
+  c->timing = enable != 0;
+  return 0;
+}
+
+extern "C" int dqmc_checks(dqmc_ctx* c, double* max_propagation_error, int64_t* nonreal) {
+  CU(c, cudaSetDevice(c->p.device));
+  double chk[2]; int flags[2];
+  CU(c, cudaMemcpyAsync(chk, c->d_check, sizeof(chk), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemsetAsync(c->d_check, 0, sizeof(double) * 2, c->st));
+  CU(c, cudaMemsetAsync(c->d_flags + 1, 0, sizeof(int), c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  if (max_propagation_error) *max_propagation_error = chk[0];
+  if (nonreal) *nonreal = flags[1];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- bench / test hooks
+typedef int (*cublasCreate_t)(void**);
+typedef int (*cublasDestroy_t)(void*);
+typedef int (*cublasSetStream_t)(void*, cudaStream_t);
+typedef int (*cublasZgemm_t)(void*, int, int, int, int, int, const cplx*, const cplx*, int, const cplx*, int, const cplx*, cplx*, int);
+
+extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_per_launch) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int n = c->n;
+  const size_t nn = (size_t)n * n;
+  cudaEvent_t e0, e1;
+  CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+  const bool timing_saved = c->timing;
+  c->timing = false;
+  void* blas = nullptr; void* handle = nullptr; cublasZgemm_t zg = nullptr; cublasDestroy_t zdestroy = nullptr;
+  if (which == 2) {
+    blas = dlopen("libcublas.so.12", RTLD_NOW | RTLD_LOCAL);
+    if (!blas) blas = dlopen("libcublas.so", RTLD_NOW | RTLD_LOCAL);
+    if (!blas) { c->timing = timing_saved; CTX_FAIL(c, "cuBLAS not found (peak probe only): %s", dlerror()); }
+    cublasCreate_t zc = (cublasCreate_t)dlsym(blas, "cublasCreate_v2");
+    cublasSetStream_t zs = (cublasSetStream_t)dlsym(blas, "cublasSetStream_v2");
+    zg = (cublasZgemm_t)dlsym(blas, "cublasZgemm_v2");
+    zdestroy = (cublasDestroy_t)dlsym(blas, "cublasDestroy_v2");
+    if (!zc || !zs || !zg || zc(&handle) != 0 || zs(handle, c->st) != 0) { c->timing = timing_saved; CTX_FAIL(c, "cuBLAS init failed"); }
+  }
+  if (which == 0 || which == 5 || which == 7) NEED_OPS(c);
+  long long pos_saved = 0;
+  const int slice_saved = c->current_slice;
+  if (which == 5) {
+    CU(c, cudaMemcpyAsync(&pos_saved, c->d_pos, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(c->W[4], c->G, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->hs_bak, c->hs, sizeof(double) * 3 * c->N * c->M, cudaMemcpyDeviceToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    c->current_slice = 1;
+  }
+  int rc = 0;
+  for (int it = -1; it < reps && rc == 0; ++it) {     // it == -1: warm-up
+    if (it == 0) CU(c, cudaEventRecord(e0, c->st));
+    switch (which) {
+      case 0: rc = wrap_greens_dev(c, c->W[4], 1, 1); break;
+      case 1: rc = zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[0], n, c->W[1], n, ZERO, c->W[2], n, c->num_sms); break;
+      case 2: rc = zg(handle, 0, 0, n, n, n, &ONE, c->W[0], n, c->W[1], n, &ZERO, c->W[2], n); break;
+      case 3:
+        rc = cudaMemcpyAsync(c->W[0], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
+        if (!rc) rc = colnorm2(c->st, c->W[0], n, n, c->colnorm);
+        if (!rc) rc = udt_dev(c, c->W[3], c->dabs);
+        break;
+      case 4: rc = calculate_greens_dev(c); break;
+      case 5: {
+        CU(c, cudaMemsetAsync(c->d_pos, 0, sizeof(long long), c->st));
+        rc = local_updates_dev(c, 0.5);
+        break;
+      }
+      case 6: rc = cudaMemcpyAsync(c->W[0], c->W[1], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess; break;
+      case 7: {
+        Chain ch; ch.nsteps = 0;
+        for (int k = 0; k < c->sm && ch.nsteps + 4 <= DQMC_MAX_CHAIN; ++k) push_B(c, ch, DQMC_B_LEFT, 1 + k);
+        rc = run_chain(c, false, c->W[4], ch, nullptr, c->colnorm);
+        break;
+      }
+      default: rc = -1; snprintf(g_errbuf, sizeof(g_errbuf), "dqmc_bench_kernel: unknown kernel %d", which);
+    }
+  }
+  if (rc == 0) {
+    CU(c, cudaEventRecord(e1, c->st));
+    CU(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+  }
+  if (which == 5) {
+    CU(c, cudaMemcpyAsync(c->G, c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->hs, c->hs_bak, sizeof(double) * 3 * c->N * c->M, cudaMemcpyDeviceToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->d_pos, &pos_saved, sizeof(long long), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    c->current_slice = slice_saved;
+  }
+  if (handle && zdestroy) zdestroy(handle);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  c->timing = timing_saved;
+  if (rc) { memcpy(c->err, g_errbuf, sizeof(g_errbuf)); return -1; }
+  return 0;
+}
+
+extern "C" int dqmc_test_zgemm(dqmc_ctx* c, int opA, int opB, int M, int N, int K, const double* alpha, const double* A,
+                               int lda, const double* B, int ldb, const double* beta, double* C, int ldc) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int acols = opA == OP_N ? K : M, bcols = opB == OP_N ? N : K;
+  cplx *dA, *dB, *dC;
+  CU(c, cudaMalloc((void**)&dA, sizeof(cplx) * (size_t)lda * acols));
+  CU(c, cudaMalloc((void**)&dB, sizeof(cplx) * (size_t)ldb * bcols));
+  CU(c, cudaMalloc((void**)&dC, sizeof(cplx) * (size_t)ldc * N));
+  CU(c, cudaMemcpy(dA, A, sizeof(cplx) * (size_t)lda * acols, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(dB, B, sizeof(cplx) * (size_t)ldb * bcols, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(dC, C, sizeof(cplx) * (size_t)ldc * N, cudaMemcpyHostToDevice));
+  int rc = zgemm(c->st, opA, opB, M, N, K, cmake(alpha[0], alpha[1]), dA, lda, dB, ldb, cmake(beta[0], beta[1]), dC, ldc, c->num_sms);
+  cudaError_t e = cudaStreamSynchronize(c->st);
+  if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(cplx) * (size_t)ldc * N, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  if (rc) { memcpy(c->err, g_errbuf, sizeof(g_errbuf)); return -1; }
+  if (e != cudaSuccess) CTX_FAIL(c, "dqmc_test_zgemm: %s", cudaGetErrorString(e));
+  return 0;
+}

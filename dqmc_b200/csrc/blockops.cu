@@ -1,0 +1,163 @@
+#include "blockops.cuh"
+
+// One CTA stages `nvec` vectors of length n (columns for COLS, rows for ROWS) in shared memory,
+// applies every step of the chain in place, and writes them back.
+template <bool ROWS>
+__global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat, int n, int ld, int nvec_cta,
+                                                          Chain chain, const double* __restrict__ hsfield,
+                                                          int nsites, double lam_dtau,
+                                                          const double* __restrict__ colscale,
+                                                          double* __restrict__ colnorm2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ldx = ROWS ? n + 1 : n;
+  cplx* x = reinterpret_cast<cplx*>(smem_raw);
+  double4* tab = reinterpret_cast<double4*>(x + (size_t)nvec_cta * ldx);
+  __shared__ double red[8];
+
+  const int v0 = blockIdx.x * nvec_cta;
+  const int nvec = min(nvec_cta, n - v0);
+  const int tid = threadIdx.x;
+
+  // ---- global -> shared
+  if (!ROWS) {
+    for (int v = 0; v < nvec; ++v)
+      for (int j = tid; j < n; j += blockDim.x) x[(size_t)v * ldx + j] = mat[(size_t)(v0 + v) * ld + j];
+  } else {
+    // element (row v0+v, col j): v fastest so that each column contributes nvec*16 contiguous bytes
+    const int tot = nvec * n;
+    for (int e = tid; e < tot; e += blockDim.x) {
+      int v = e % nvec, j = e / nvec;
+      x[(size_t)v * ldx + j] = mat[(size_t)j * ld + v0 + v];
+    }
+  }
+  __syncthreads();
+
+  for (int st = 0; st < chain.nsteps; ++st) {
+    const ChainStep s = chain.s[st];
+    if (s.kind == 0) {
+      for (int b = tid; b < s.nblk; b += blockDim.x) {
+        int i0 = s.idx[4 * b + 0], i1 = s.idx[4 * b + 1], i2 = s.idx[4 * b + 2], i3 = s.idx[4 * b + 3];
+        cplx m[4][4];
+        const cplx* vp = s.val + 16 * (size_t)b;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            cplx t = (s.mode == OP_N || s.mode == OP_J) ? vp[4 * r + c] : vp[4 * c + r];
+            if (s.mode == OP_C || s.mode == OP_J) t.y = -t.y;
+            m[r][c] = t;
+          }
+        for (int v = 0; v < nvec; ++v) {
+          cplx* xv = x + (size_t)v * ldx;
+          cplx a0 = xv[i0], a1 = xv[i1], a2 = xv[i2], a3 = xv[i3];
+          cplx y[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            cplx acc = cmul(m[r][0], a0);
+            cfma(acc, m[r][1], a1);
+            cfma(acc, m[r][2], a2);
+            cfma(acc, m[r][3], a3);
+            y[r] = acc;
+          }
+          xv[i0] = y[0]; xv[i1] = y[1]; xv[i2] = y[2]; xv[i3] = y[3];
+        }
+      }
+      __syncthreads();
+    } else {
+      // interaction exponential of one time slice (interactions.jl:35-88):
+      // C = cosh(lam*dtau*|phi|), S = (i phi2 - phi1) sign sinh/|phi|, R = -phi3 sign sinh/|phi|
+      for (int i = tid; i < nsites; i += blockDim.x) {
+        const double* h = hsfield + 3 * ((size_t)i + (size_t)nsites * s.slice);
+        double p1 = h[0], p2 = h[1], p3 = h[2];
+        double nrm = sqrt(p1 * p1 + p2 * p2 + p3 * p3);
+        double sh = s.sign * sinh(lam_dtau * nrm) / nrm;
+        double sim = p2 * sh;
+        if (s.mode == OP_T || s.mode == OP_J) sim = -sim;  // E^T = conj(E) (E is Hermitian)
+        tab[i] = make_double4(cosh(lam_dtau * nrm), -p1 * sh, sim, -p3 * sh);
+      }
+      __syncthreads();
+      for (int i = tid; i < nsites; i += blockDim.x) {
+        double4 t = tab[i];
+        const double C = t.x, R = t.w;
+        const cplx S = cmake(t.y, t.z), cS = cmake(t.y, -t.z);
+        for (int v = 0; v < nvec; ++v) {
+          cplx* xv = x + (size_t)v * ldx;
+          cplx a0 = xv[i], a1 = xv[i + nsites], a2 = xv[i + 2 * nsites], a3 = xv[i + 3 * nsites];
+          cplx y0 = cscale(a0, C); cfma(y0, S, a1); y0.x = fma(R, a3.x, y0.x); y0.y = fma(R, a3.y, y0.y);
+          cplx y1 = cscale(a1, C); cfma(y1, cS, a0); y1.x = fma(-R, a2.x, y1.x); y1.y = fma(-R, a2.y, y1.y);
+          cplx y2 = cscale(a2, C); cfma(y2, cS, a3); y2.x = fma(-R, a1.x, y2.x); y2.y = fma(-R, a1.y, y2.y);
+          cplx y3 = cscale(a3, C); cfma(y3, S, a2); y3.x = fma(R, a0.x, y3.x); y3.y = fma(R, a0.y, y3.y);
+          xv[i] = y0; xv[i + nsites] = y1; xv[i + 2 * nsites] = y2; xv[i + 3 * nsites] = y3;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- shared -> global (optionally scale columns and emit their squared norms)
+  if (!ROWS) {
+    for (int v = 0; v < nvec; ++v) {
+      const double sc = colscale ? colscale[v0 + v] : 1.0;
+      double acc = 0.0;
+      for (int j = tid; j < n; j += blockDim.x) {
+        cplx t = cscale(x[(size_t)v * ldx + j], sc);
+        acc += cabs2(t);
+        mat[(size_t)(v0 + v) * ld + j] = t;
+      }
+      if (colnorm2) {
+        acc = warp_sum(acc);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+          double t = 0.0;
+          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+          colnorm2[v0 + v] = t;
+        }
+      }
+    }
+  } else {
+    const int tot = nvec * n;
+    for (int e = tid; e < tot; e += blockDim.x) {
+      int v = e % nvec, j = e / nvec;
+      mat[(size_t)j * ld + v0 + v] = x[(size_t)v * ldx + j];
+    }
+  }
+}
+
+int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, const double* hsfield,
+                       int nsites, double lam_dtau, const double* colscale, double* colnorm2,
+                       int num_sms, cudaStream_t stream) {
+  const size_t smem_cap = 200 * 1024;
+  const size_t tab_bytes = sizeof(double4) * (size_t)nsites;
+  const int ldx = rows ? n + 1 : n;
+  int nvec_max = (int)((smem_cap - tab_bytes) / (sizeof(cplx) * (size_t)ldx));
+  if (nvec_max < 1) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "apply_chain: n=%d too large for one shared-memory vector", n);
+    return -1;
+  }
+  int nvec;
+  if (rows) {
+    nvec = 8;                                   // 128 B contiguous per column
+    while (nvec > 1 && ((n + nvec - 1) / nvec < num_sms / 2 || nvec > nvec_max)) nvec >>= 1;
+  } else {
+    nvec = (n + num_sms - 1) / num_sms;
+    if (nvec > nvec_max) nvec = nvec_max;
+    if (nvec < 1) nvec = 1;
+  }
+  const int grid = (n + nvec - 1) / nvec;
+  const size_t smem = sizeof(cplx) * (size_t)nvec * ldx + tab_bytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(apply_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(apply_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  if (rows)
+    apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2);
+  else
+    apply_chain_kernel<false><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}

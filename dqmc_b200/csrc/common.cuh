@@ -1,0 +1,88 @@
+// Shared device/host helpers for libdqmc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+typedef double2 cplx;  // interleaved (re, im) == Julia ComplexF64
+
+#define DQMC_HD __host__ __device__ __forceinline__
+#define DQMC_D __device__ __forceinline__
+
+DQMC_HD cplx cmake(double r, double i) { return make_double2(r, i); }
+DQMC_HD cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+DQMC_HD cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+DQMC_HD cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+DQMC_HD cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+DQMC_HD cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+DQMC_HD cplx cneg(cplx a) { return make_double2(-a.x, -a.y); }
+// acc += a*b
+DQMC_HD void cfma(cplx& acc, cplx a, cplx b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+DQMC_HD void cfma_conj(cplx& acc, cplx a, cplx b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+DQMC_HD cplx cdiv(cplx a, cplx b) {
+  double d = b.x * b.x + b.y * b.y;
+  return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+DQMC_HD double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+enum { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };  // none, transpose, conj-transpose, conj
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      snprintf(g_errbuf, sizeof(g_errbuf), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,    \
+               cudaGetErrorString(_e));                                                     \
+      return -1;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+extern char g_errbuf[512];
+extern long long g_launches;   // kernels launched by this library (all contexts)
+
+// FP64 tensor-core MMA (DMMA.8x8x4): D(8x8) += A(8x4,row) * B(4x8,col).
+// lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4], d0/d1 = D[lane/4][2*(lane%4) + {0,1}].
+DQMC_D void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+DQMC_D double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DQMC_D double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Grid-wide barrier for kernels launched cooperatively (all CTAs co-resident).
+// `bar` points to two zero-initialised unsigned ints {count, generation}.
+DQMC_D void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    unsigned int g = *gen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) { }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}

@@ -1,0 +1,28 @@
+// Persistent local-update kernel: the serial Metropolis loop over the sites of one time slice
+// (local_updates.jl:1-39) with delayed rank-4 Woodbury updates of the equal-time Green's function
+// (calc_detratio :42-59, update_greens! :61-95).
+#pragma once
+#include "common.cuh"
+
+struct LUArgs {
+  int n, nsites, nslices, slice;   // slice 0-based
+  int kmax;                        // accepted updates batched before G is flushed with one GEMM
+  int rpc;                         // rows of A / columns of B owned by each CTA
+  int edrun;
+  double box, dtau, lam_dtau, inv_dtau_c2, r, u;
+  cplx* G;                         // n x n, column-major
+  cplx* At;                        // [4*kmax x n]  At[p + ldk*row] = A[row,p]
+  cplx* Bm;                        // [4*kmax x n]  Bm[p + ldk*col] = B[p,col]
+  double* hs;                      // hsfield [3, nsites, nslices]
+  const int* nbr;                  // [4, nsites] 0-based spatial neighbours
+  const double* unif;              // uniform stream
+  long long nunif;
+  long long* pos;                  // in/out: next unread position in unif
+  long long* accepted;             // in/out: accumulated accepted proposals
+  double* dS;                      // in/out: accumulated -log(exp(-dS)) of accepted proposals
+  int* flags;                      // [0] stream exhausted, [1] non-real determinant ratios seen
+  unsigned int* bar;               // grid barrier state {count, generation}
+};
+
+int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid);
+int local_updates_grid(int n, int num_sms, int* rpc);

@@ -1,0 +1,21 @@
+// Blocked Householder QR (compact WY), explicit-Q formation, and a fused multi-RHS triangular solve,
+// all complex FP64.  Replaces the reference's LAPACK call sites on the stabilization path:
+// zgeqp3 + zungqr inside decompose_udt! (linalg.jl:20-39) and the LU solve / inverse of
+// calculate_greens (stack.jl:355-361, linalg.jl:61).  Pivoting is a one-off column sort by norm
+// before the factorization ("stabilization algebra").
+#pragma once
+#include "common.cuh"
+
+#define QR_NB 32      // panel width
+#define QR_CL 8       // CTAs per thread-block cluster in the panel factorization
+
+// Householder QR of the n x n matrix A (in place: R in the upper triangle, V below, tau, |R_ii| in dabs).
+// tfac receives ceil(n/32) compact-WY T factors (32x32, column-major, ld 32).  If rhs != nullptr,
+// Q^H is applied to the n x nrhs matrix rhs as the factorization proceeds.
+int qr_factor(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac,
+              cplx* rhs, int ldr, int nrhs, int num_sms);
+// Q (n x n, explicit) from the output of qr_factor.
+int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, cplx* Q, int ldq, int num_sms);
+// X = R^{-1} Y in place in Y (n x nrhs); R = upper triangle of A.  work: ceil(n/32)*1024 cplx.
+int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
+               const double* rowscale, int num_sms);

@@ -1,0 +1,128 @@
+#include "zgemm.cuh"
+
+// Operand tiles live in shared memory in *fragment order*: for every (k-step of 4, tile of 8 rows/cols)
+// the 32 lanes' elements are contiguous, element `lane` being X[o = lane/4][k = lane%4] as (re,im).
+// A fragment load is then one conflict-free LDS.128 per lane, and the global->shared copy reads
+// 128 B (op N on A / op T,C on B) or 64 B (the other cases) contiguous segments.
+//
+// One complex 8x8x4 tile product = 4 real DMMAs:  Cr += Ar*Br - Ai*Bi,  Ci += Ar*Bi + Ai*Br.
+template <int WTM, int WTN, int NWM, int NWN>
+__global__ void __launch_bounds__(NWM * NWN * 32)
+zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int lda, int opA,
+             const cplx* __restrict__ B, int ldb, int opB, cplx beta, cplx* __restrict__ C, int ldc) {
+  constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8, KT = 8, KS = KT / 4;
+  constexpr int NW = NWM * NWN;
+  constexpr int FA = (BM / 8) * KS, FB = (BN / 8) * KS;       // fragments per stage
+  constexpr int LA = (FA + NW - 1) / NW, LB = (FB + NW - 1) / NW;
+  __shared__ __align__(16) cplx As[FA * 32];
+  __shared__ __align__(16) cplx Bs[FB * 32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp % NWM, wn = warp / NWM;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int lo = lane >> 2, lk = lane & 3;
+
+  double cr[WTM][WTN][2], ci[WTM][WTN][2];
+#pragma unroll
+  for (int i = 0; i < WTM; ++i)
+#pragma unroll
+    for (int j = 0; j < WTN; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+  cplx ra[LA], rb[LB];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < LA; ++t) {
+      int f = warp + t * NW;
+      cplx v = cmake(0.0, 0.0);
+      if (f < FA) {
+        int kk = f / (BM / 8), rt = f % (BM / 8);
+        int row = m0 + rt * 8 + lo, k = k0 + kk * 4 + lk;
+        if (row < M && k < K) {
+          if (opA == OP_N) v = A[(size_t)k * lda + row];
+          else { v = A[(size_t)row * lda + k]; if (opA == OP_C) v.y = -v.y; }
+        }
+      }
+      ra[t] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < LB; ++t) {
+      int f = warp + t * NW;
+      cplx v = cmake(0.0, 0.0);
+      if (f < FB) {
+        int kk = f / (BN / 8), ct = f % (BN / 8);
+        int col = n0 + ct * 8 + lo, k = k0 + kk * 4 + lk;
+        if (col < N && k < K) {
+          if (opB == OP_N) v = B[(size_t)col * ldb + k];
+          else { v = B[(size_t)k * ldb + col]; if (opB == OP_C) v.y = -v.y; }
+        }
+      }
+      rb[t] = v;
+    }
+  };
+
+  gload(0);
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < LA; ++t) { int f = warp + t * NW; if (f < FA) As[f * 32 + lane] = ra[t]; }
+#pragma unroll
+    for (int t = 0; t < LB; ++t) { int f = warp + t * NW; if (f < FB) Bs[f * 32 + lane] = rb[t]; }
+    __syncthreads();
+    if (k0 + KT < K) gload(k0 + KT);
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      cplx a[WTM], b[WTN];
+#pragma unroll
+      for (int i = 0; i < WTM; ++i) a[i] = As[(kk * (BM / 8) + wm * WTM + i) * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < WTN; ++j) b[j] = Bs[(kk * (BN / 8) + wn * WTN + j) * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < WTM; ++i)
+#pragma unroll
+        for (int j = 0; j < WTN; ++j) {
+          dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+          dmma884(cr[i][j][0], cr[i][j][1], -a[i].y, b[j].y);
+          dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+          dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+        }
+    }
+  }
+
+  const bool use_c = (beta.x != 0.0 || beta.y != 0.0);
+#pragma unroll
+  for (int i = 0; i < WTM; ++i)
+#pragma unroll
+    for (int j = 0; j < WTN; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int row = m0 + (wm * WTM + i) * 8 + lo;
+        int col = n0 + (wn * WTN + j) * 8 + 2 * lk + e;
+        if (row < M && col < N) {
+          cplx acc = cmul(alpha, cmake(cr[i][j][e], ci[i][j][e]));
+          cplx* p = C + (size_t)col * ldc + row;
+          if (use_c) cfma(acc, beta, *p);
+          *p = acc;
+        }
+      }
+}
+
+int zgemm(cudaStream_t stream, int opA, int opB, int M, int N, int K, cplx alpha, const cplx* A, int lda,
+          const cplx* B, int ldb, cplx beta, cplx* C, int ldc, int num_sms) {
+  if (M <= 0 || N <= 0) return 0;
+  if (opA == OP_J || opB == OP_J) { snprintf(g_errbuf, sizeof(g_errbuf), "zgemm: OP_J unsupported"); return -1; }
+  auto tiles = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
+  const long want = (long)num_sms * 3 / 4;
+  if (tiles(128, 64) >= want) {
+    dim3 g((M + 127) / 128, (N + 63) / 64);
+    zgemm_kernel<4, 4, 4, 2><<<g, 256, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
+  } else if (tiles(64, 64) >= want) {
+    dim3 g((M + 63) / 64, (N + 63) / 64);
+    zgemm_kernel<4, 2, 2, 4><<<g, 256, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
+  } else {
+    dim3 g((M + 31) / 32, (N + 31) / 32);
+    zgemm_kernel<2, 2, 2, 2><<<g, 128, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
+  }
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}

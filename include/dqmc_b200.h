@@ -1,0 +1,125 @@
+/*
+ * libdqmc_b200 — C ABI of the B200-native DQMC hot path (local-update sweep, Green's-function wrap,
+ * UDT stabilization) for the O(3) spin-fermion model.
+ *
+ * The reference (carstenbauer/dqmc, pure Julia) has no FFI: its seam is multiple dispatch on
+ * AbstractDQMC{C<:Checkerboard} (src/dqmc_framework.jl:4-13).  Every entry point below names the reference
+ * function it replaces; INTEGRATION.md shows the Julia `ccall` methods a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; complex arrays are interleaved (re,im) doubles, column-major
+ * (bit-identical to Julia's Array{ComplexF64}); `site` and `slice` arguments are 1-based like the reference;
+ * every call returns 0 on success and a negative code on error (message: dqmc_last_error).  A dqmc_ctx is
+ * bound to one device and one stream and is not thread-safe (the reference driver is single-threaded,
+ * app/dqmc.jl:29-37).  There is no CPU fallback: without a CUDA device dqmc_create fails.
+ */
+#ifndef DQMC_B200_H
+#define DQMC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dqmc_ctx dqmc_ctx;
+
+/* POD mirror of the fields of `Params` (src/parameters.jl:4-80) and `Lattice` (src/lattice.jl:1-55) the path reads. */
+typedef struct {
+  int32_t L;            /* linear size; sites = L*L (lattice.jl:3-4) */
+  int32_t flv;          /* 4 (O(3)); flv = 2 models are not implemented */
+  int32_t opdim;        /* 3 */
+  int32_t slices;       /* M = beta / delta_tau (parameters.jl:102-110) */
+  int32_t safe_mult;    /* slices between stabilizations (parameters.jl:111) */
+  int32_t edrun;        /* only the mass term of the boson action (action.jl:94) */
+  int32_t all_checks;   /* compare wrapped vs fresh G at each stabilization (stack.jl:416-429, 469-480) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t delay;        /* accepted local updates batched per G flush (0 = default 16) */
+  int32_t reserved;
+  double delta_tau, lambda, r, c, u;
+} dqmc_params;
+
+/* sparse factors taken from mc.l (lattice.jl:24-47), as Julia SparseMatrixCSC (Int64, 1-based) */
+enum {
+  DQMC_OP_HOP_HALF_B = 0,      /* l.chkr_hop_half[2]      */
+  DQMC_OP_HOP_A = 1,           /* l.chkr_hop[1]           */
+  DQMC_OP_HOP_HALF_INV_B = 2,  /* l.chkr_hop_half_inv[2]  */
+  DQMC_OP_HOP_INV_A = 3,       /* l.chkr_hop_inv[1]       */
+  DQMC_OP_MU = 4,              /* l.chkr_mu               */
+  DQMC_OP_MU_INV = 5,          /* l.chkr_mu_inv           */
+  DQMC_OP_COUNT = 6
+};
+
+/* dqmc_multiply_B op codes (slice_matrices.jl:101-226) */
+enum { DQMC_B_LEFT = 0, DQMC_B_RIGHT = 1, DQMC_B_INV_LEFT = 2, DQMC_B_INV_RIGHT = 3, DQMC_B_DAGGER_LEFT = 4 };
+
+/* replaces initialize_stack (stack.jl:224-242): allocates every device buffer of Stack{G} (stack.jl:45-118) */
+int dqmc_create(dqmc_ctx** out, const dqmc_params* p);
+int dqmc_destroy(dqmc_ctx* ctx);
+const char* dqmc_last_error(dqmc_ctx* ctx);   /* ctx may be NULL: last global error */
+
+/* data of init_checkerboard_matrices[_Bfield] (hoppings_checkerboard.jl:65-136,165-270); copied */
+int dqmc_set_operator(dqmc_ctx* ctx, int which, int64_t m, int64_t n, const int64_t* colptr,
+                      const int64_t* rowval, const void* nzval, int nz_is_complex);
+/* l.neighbors [4,N] (lattice.jl:112-117), 1-based; time neighbours are periodic (lattice.jl:144-153) */
+int dqmc_set_neighbors(dqmc_ctx* ctx, const int64_t* neighbors);
+
+/* mc.p.hsfield [opdim,N,M] Float64 (parameters.jl:19) */
+int dqmc_set_hsfield(dqmc_ctx* ctx, const double* h);
+int dqmc_get_hsfield(dqmc_ctx* ctx, double* h);
+/* mc.s.greens [n,n] ComplexF64 (stack.jl:55) */
+int dqmc_set_greens(dqmc_ctx* ctx, const double* g);
+int dqmc_get_greens(dqmc_ctx* ctx, double* g);
+/* mc.s.current_slice / mc.s.direction (stack.jl:391-499); slice in 0..M+1 */
+int dqmc_get_state(dqmc_ctx* ctx, int32_t* slice, int32_t* direction);
+int dqmc_set_state(dqmc_ctx* ctx, int32_t slice, int32_t direction);
+
+/* build_stack (stack.jl:251-272) */
+int dqmc_build_stack(dqmc_ctx* ctx);
+/* propagate (stack.jl:391-499); returns the new (current_slice, direction) */
+int dqmc_propagate(dqmc_ctx* ctx, int32_t* slice, int32_t* direction);
+/* wrap_greens! (stack.jl:316-325) on mc.s.greens (g == NULL) or on a caller-owned host matrix */
+int dqmc_wrap_greens(dqmc_ctx* ctx, double* g_or_null, int32_t slice, int32_t direction);
+/* multiply_B_left!/right!/inv_left!/inv_right!/daggered_B_left! (slice_matrices.jl:101-226) on a host n x n matrix */
+int dqmc_multiply_B(dqmc_ctx* ctx, int op, int32_t slice, double* m);
+/* calculate_greens (stack.jl:338-369) from caller-supplied UDTs (host) into mc.s.greens; also returns it if g != NULL */
+int dqmc_calculate_greens_from(dqmc_ctx* ctx, const double* Ul, const double* Dl, const double* Tl,
+                               const double* Ur, const double* Dr, const double* Tr, double* g_or_null);
+/* calculate_logdet (stack.jl:377-385) of the last calculate_greens */
+int dqmc_logdet(dqmc_ctx* ctx, double* logdet);
+/* decompose_udt! (linalg.jl:20-39) of a host n x n matrix: U [n,n], D [n], T [n,n] */
+int dqmc_decompose_udt(dqmc_ctx* ctx, const double* x, double* U, double* D, double* T);
+
+/* local_updates (local_updates.jl:1-39) at mc.s.current_slice.  `u` is the caller's uniform [0,1) stream, consumed
+ * in the reference's order (opdim proposal draws, then one accept draw only if p_acc <= 1); `consumed` tells the
+ * caller how far to advance its own RNG.  dS_total accumulates the change of mc.p.boson_action. */
+int dqmc_local_updates(dqmc_ctx* ctx, double box, const double* u, int64_t nu, int64_t* consumed,
+                       int64_t* accepted, double* dS_total);
+/* nupdates x { propagate; local_updates } = the body of `for u in 1:2M update(mc,i)` (dqmc_framework.jl:258-261,
+ * 500-517) without global updates.  u == NULL uses the stream uploaded with dqmc_set_uniforms. */
+int dqmc_sweep(dqmc_ctx* ctx, int32_t nupdates, double box, const double* u, int64_t nu, int64_t* consumed,
+               int64_t* accepted, double* dS_total);
+int dqmc_set_uniforms(dqmc_ctx* ctx, const double* u, int64_t nu);
+
+/* telemetry: phase times in ms (CUDA events): [0] wrap, [1] local updates, [2] stack UDT (add_slice_sequence),
+ * [3] calculate_greens, [4] total of dqmc_sweep; resets the accumulators.  Replaces the @mytimeit labels
+ * (slice_matrices.jl:105-125, local_updates.jl:47,68, stack.jl:256,290,344). */
+int dqmc_timers(dqmc_ctx* ctx, double* ms, int32_t n);
+int dqmc_set_timing(dqmc_ctx* ctx, int32_t enable);   /* phase timers are off by default */
+/* largest |G_wrapped - G_fresh| seen since the last call (the reference prints it when > 1e-7, stack.jl:426,477);
+ * nonreal = number of proposals with |Im/Re| of the determinant ratio > 1e-4 (local_updates.jl:19-20) */
+int dqmc_checks(dqmc_ctx* ctx, double* max_propagation_error, int64_t* nonreal);
+int dqmc_sync(dqmc_ctx* ctx);
+
+/* --- measurement hooks used by bench.py (not part of the reference's interface) --- */
+/* time `reps` launches of one kernel group with CUDA events on the context's stream; returns ms per launch.
+ * which: 0 wrap (+1, current slice), 1 ZGEMM n x n x n (hand-written DMMA), 2 cuBLAS ZGEMM n^3 (peak probe, dlopen),
+ * 3 UDT (sort+QR+Q+T), 4 calculate_greens, 5 local_updates on slice 1 with the uploaded uniforms (state restored),
+ * 6 device copy of G (HBM probe), 7 add_slice_sequence B-chain (safe_mult slices) */
+int dqmc_bench_kernel(dqmc_ctx* ctx, int which, int reps, double* ms_per_launch);
+/* C = alpha*op(A)*op(B) + beta*C on host matrices through the hand-written kernel (test hook); op: 0 N, 1 T, 2 C */
+int dqmc_test_zgemm(dqmc_ctx* ctx, int opA, int opB, int M, int N, int K, const double* alpha, const double* A, int lda,
+                    const double* B, int ldb, const double* beta, double* C, int ldc);
+int64_t dqmc_kernel_launches(dqmc_ctx* ctx);   /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,114 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol the header declares,
+fails loudly without a device, and the chain-pooling reduction works across 2 gloo ranks."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    from dqmc_b200 import lib
+    return lib
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "dqmc_b200.h")).read()
+    declared = set(re.findall(r"\b(dqmc_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dqmc_b200.h but not exported"
+    assert declared == set(built.SIGNATURES), declared ^ set(built.SIGNATURES)
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dqmc_b200 import DQMC, Params, DqmcError
+    with pytest.raises(DqmcError, match="no CUDA device|CUDA"):
+        DQMC(Params(L=4, slices=10))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dqmc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_params_from_reference_xml(tmp_path):
+    from dqmc_b200 import Params
+    xml = tmp_path / "p.in.xml"
+    xml.write_text("""<SIMULATION><PARAMETERS>
+      <PARAMETER name="L">4</PARAMETER><PARAMETER name="SLICES">10</PARAMETER>
+      <PARAMETER name="DELTA_TAU">0.1</PARAMETER><PARAMETER name="WARMUP">100</PARAMETER>
+      <PARAMETER name="SWEEPS">400</PARAMETER><PARAMETER name="SAFE_MULT">10</PARAMETER>
+      <PARAMETER name="CHECKERBOARD">TRUE</PARAMETER><PARAMETER name="HOPPINGS">1.0,0.5,-0.5,-1.0</PARAMETER>
+      <PARAMETER name="MU">-0.5</PARAMETER><PARAMETER name="LAMBDA">0.5</PARAMETER><PARAMETER name="U">1.0</PARAMETER>
+      <PARAMETER name="R">2.0</PARAMETER><PARAMETER name="C">3.0</PARAMETER>
+      <PARAMETER name="GLOBAL_UPDATES">TRUE</PARAMETER><PARAMETER name="BFIELD">TRUE</PARAMETER>
+      <PARAMETER name="OPDIM">3</PARAMETER></PARAMETERS></SIMULATION>""")
+    p = Params.from_xml(str(xml))
+    assert (p.L, p.slices, p.safe_mult, p.thermalization, p.measurements) == (4, 10, 10, 50, 200)
+    assert p.Bfield and p.global_updates and p.mu1 == p.mu2 == -0.5 and p.flv == 4
+
+
+def test_product_model_matches_fixtures(golden_o3):
+    from dqmc_b200 import Params, Lattice
+    from tests.helpers import csc_dense, maxabs
+    for bf, pre in ((False, "nob_"), (True, "")):
+        l = Lattice(Params(L=4, slices=10, Bfield=bf))
+        for k in range(2):
+            for nm in ("chkr_hop", "chkr_hop_inv", "chkr_hop_half", "chkr_hop_half_inv"):
+                assert maxabs(getattr(l, nm)[k].toarray(), csc_dense(golden_o3, f"{pre}{nm}{k+1}")) < 5e-15
+        assert maxabs(l.chkr_mu.toarray(), csc_dense(golden_o3, pre + "chkr_mu")) < 1e-15
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from dqmc_b200.parallel import init_process_group, combined_mean_and_var
+rank, world = init_process_group("gloo")
+rs = np.random.RandomState(100 + rank)
+n = 50 + 10 * rank
+x = rs.rand(n, 6) + 1j * rs.rand(n, 6)
+mean, var = combined_mean_and_var(n, x.mean(0), x.var(0, ddof=1))
+allx = np.concatenate([np.random.RandomState(100 + r).rand(50 + 10 * r, 6) + 1j * np.random.RandomState(100 + r).rand(50 + 10 * r, 6) * 0 for r in range(world)])
+# rebuild every rank's sample exactly
+parts = []
+for r in range(world):
+    q = np.random.RandomState(100 + r)
+    m = 50 + 10 * r
+    parts.append(q.rand(m, 6) + 1j * q.rand(m, 6))
+allx = np.concatenate(parts)
+assert np.allclose(mean, allx.mean(0), atol=1e-12), (mean, allx.mean(0))
+assert np.allclose(var, allx.var(0, ddof=1), atol=1e-12)
+dist.barrier()
+if rank == 0:
+    print("POOL_OK")
+"""
+
+
+def test_pooled_statistics_two_ranks_gloo(tmp_path):
+    # tests_statistics.jl:3-81: pooled mean/var == mean/var of the concatenation; here across 2 processes
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "POOL_OK" in out.stdout, out.stdout + out.stderr

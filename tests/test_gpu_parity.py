@@ -1,0 +1,231 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden vectors.
+
+All tests need a B200 (`-m gpu`).  Tolerances: G after wrap / stabilization within 1e-10 relative (north star);
+single operations are held to much tighter bounds.  Integer/field work (accept/reject sequence, boson field)
+must be bit-exact for a shared uniform stream.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import JuliaMT
+from oracle.dqmc import UniformStream as OracleStream
+from tests.helpers import maxabs
+
+pytestmark = pytest.mark.gpu
+
+SEED = 4729339882041979125
+
+
+def _mk(L, M, bfield, sm=10, lam=0.5, all_checks=True, delay=0):
+    from dqmc_b200 import DQMC, Params
+    mc = DQMC(Params(L=L, slices=M, safe_mult=sm, Bfield=bfield, lambda_=lam, all_checks=all_checks), device=0, delay=delay)
+    om = oracle.OracleDQMC(oracle.Params(L=L, slices=M, safe_mult=sm, Bfield=bfield, lam=lam))
+    return mc, om
+
+
+def _rand_c(rs, *shape):
+    return rs.rand(*shape) + 1j * rs.rand(*shape)
+
+
+# ------------------------------------------------------------------------------------------ ZGEMM
+@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 256, 256), (128, 72, 40), (1024, 1024, 64), (37, 53, 29)])
+def test_zgemm_all_ops(shape):
+    mc, _ = _mk(4, 10, False)
+    rs = np.random.RandomState(0)
+    M, N, K = shape
+    for opA in (0, 1, 2):
+        for opB in (0, 1, 2):
+            A = _rand_c(rs, *((M, K) if opA == 0 else (K, M))) - 0.5
+            B = _rand_c(rs, *((K, N) if opB == 0 else (N, K))) - 0.5
+            C0 = _rand_c(rs, M, N)
+            fa = (lambda x: x, lambda x: x.T, lambda x: x.conj().T)[opA]
+            fb = (lambda x: x, lambda x: x.T, lambda x: x.conj().T)[opB]
+            alpha, beta = 0.7 - 0.2j, -0.3 + 1.1j
+            ref = alpha * (fa(A) @ fb(B)) + beta * C0
+            got = mc.test_zgemm(opA, opB, A, B, C0, alpha, beta)
+            assert maxabs(got, ref) < 1e-12 * K, (shape, opA, opB)
+    mc.close()
+
+
+# ------------------------------------------------------------------------------------------ slice matrices
+@pytest.mark.parametrize("L,bfield", [(4, False), (4, True), (8, False), (8, True)])
+def test_multiply_B_vs_oracle(L, bfield):
+    # slice_matrices.jl:101-226; tests_O3.jl:283-332
+    mc, om = _mk(L, 10, bfield)
+    rs = np.random.RandomState(1)
+    field = rs.rand(3, L * L, 10)
+    mc.hsfield = field
+    om.hsfield = field.copy()
+    n = mc.n
+    A = _rand_c(rs, n, n)
+    s = 3
+    pairs = [(mc.multiply_B_left, om.multiply_B_left), (mc.multiply_B_right, om.multiply_B_right),
+             (mc.multiply_B_inv_left, om.multiply_B_inv_left), (mc.multiply_B_inv_right, om.multiply_B_inv_right),
+             (mc.multiply_daggered_B_left, om.multiply_daggered_B_left)]
+    for f, g in pairs:
+        assert maxabs(f(s, A), g(s - 1, A.copy())) < 1e-13, f.__name__
+    I = np.eye(n, dtype=complex)
+    assert maxabs(mc.multiply_B_inv_left(s, mc.multiply_B_left(s, A)), A) < 1e-13
+    assert maxabs(mc.multiply_B_inv_right(s, mc.multiply_B_right(s, A)), A) < 1e-13
+    assert maxabs(mc.multiply_B_inv_right(s, mc.multiply_B_left(s, I)), I) < 1e-13
+    B = mc.slice_matrix(s, 1.0)
+    assert maxabs(mc.multiply_daggered_B_left(s, A), B.conj().T @ A) < 1e-12
+    mc.close()
+
+
+def test_slice_matrix_golden(golden_o3):
+    # tests_O3.jl:301-304: Bplus / Bminus of the B-field model at slice 3 with the seeded start field
+    mc, _ = _mk(4, 10, True)
+    mc.hsfield = JuliaMT(SEED).rand_array(3, 16, 10)
+    assert maxabs(mc.slice_matrix(3, 1.0), golden_o3["Bplus"]) < 1e-14
+    assert maxabs(mc.slice_matrix(3, -1.0), golden_o3["Bminus"]) < 1e-14
+    mc.close()
+
+
+def test_wrap_greens_vs_oracle():
+    mc, om = _mk(8, 20, False)
+    rs = np.random.RandomState(2)
+    field = rs.rand(3, 64, 20)
+    mc.hsfield = field
+    om.hsfield = field.copy()
+    g = _rand_c(rs, mc.n, mc.n)
+    for slc, d in ((5, 1), (5, -1), (20, 1), (2, -1)):
+        assert maxabs(mc.wrap_greens(g, slc, d), om.wrap_greens(g.copy(), slc - 1, d)) < 1e-12
+    mc.close()
+
+
+# ------------------------------------------------------------------------------------------ linear algebra
+@pytest.mark.parametrize("L", [4, 8])
+def test_decompose_udt_properties(L):
+    # tests_linalg.jl:37-60: unitarity, U*D*T == X, D > 0 — on a matrix graded over 60 orders of magnitude
+    mc, _ = _mk(L, 10, False)
+    n = mc.n
+    rs = np.random.RandomState(3)
+    X = _rand_c(rs, n, n) - (0.5 + 0.5j)
+    X = X * np.logspace(20, -40, n)[rs.permutation(n)][None, :]
+    U, D, T = mc.decompose_udt(X)
+    assert maxabs(U.conj().T @ U, np.eye(n)) < 1e-13
+    assert np.all(D > 0)
+    rec = (U * D[None, :]) @ T
+    assert np.max(np.abs(rec - X) / np.linalg.norm(X, axis=0)[None, :]) < 1e-13
+    assert np.all(np.diff(D) <= 1e-12 * D[:-1])            # graded like a pivoted QR
+    assert np.linalg.cond(T) < 1e6
+    mc.close()
+
+
+def test_calculate_greens_golden(golden_o3):
+    # tests_O3.jl:215-230: dumped Ur,Dr,Tr,Ul,Dl,Tl -> dumped greens, and the logdet
+    mc, om = _mk(4, 10, True)
+    g = mc.calculate_greens(*(golden_o3[k] for k in ("Ul", "Dl", "Tl", "Ur", "Dr", "Tr")))
+    assert maxabs(g, golden_o3["greens"]) < 1e-12
+    assert np.isclose(mc.log_det, np.linalg.slogdet(golden_o3["greens"])[1], rtol=1e-10, atol=1e-10)
+    mc.close()
+
+
+# ------------------------------------------------------------------------------------------ stack / propagation
+@pytest.mark.parametrize("bfield", [False, True])
+def test_init_and_propagation_vs_oracle(bfield):
+    # tests_O3.jl:240-263: every slice of an up-down sweep; here against the oracle's own propagation (K = 5)
+    mc, om = _mk(4, 50, bfield)
+    field = JuliaMT(11).rand_array(3, 16, 50)
+    mc.init(field)
+    om.init(field)
+    assert (mc.current_slice, mc.direction) == (om.current_slice + 1, om.direction) == (50, -1)
+    assert maxabs(mc.greens, om.greens) < 1e-10
+    worst = 0.0
+    for _ in range(100):
+        s, d = mc.propagate()
+        om.propagate()
+        assert (s, d) == (om.current_slice + 1, om.direction)
+        worst = max(worst, maxabs(mc.greens, om.greens))
+    assert worst < 1e-10
+    err, _ = mc.checks()
+    assert err < 1e-9          # wrapped vs fresh G at every stabilization (reference flags > 1e-7, stack.jl:426)
+    mc.close()
+
+
+def test_propagation_to_slice_one_golden(golden_o3):
+    # tests_O3.jl:240-249
+    mc, _ = _mk(4, 10, True)
+    mc.init(JuliaMT(SEED).rand_array(3, 16, 10))
+    while mc.current_slice != 1:
+        mc.propagate()
+    mc.propagate()
+    assert mc.direction == 1 and mc.current_slice == 1
+    assert maxabs(mc.greens, golden_o3["greens"]) < 1e-11
+    mc.close()
+
+
+# ------------------------------------------------------------------------------------------ local updates
+def test_local_updates_golden(golden_o3):
+    # tests_O3.jl:179-194 with Julia's own random stream: acceptance 0.6875, bit-exact field, greens, boson action
+    from dqmc_b200 import UniformStream
+    mc, _ = _mk(4, 10, True)
+    mc.init(JuliaMT(SEED).rand_array(3, 16, 10))
+    assert mc.current_slice == 10
+    mc.greens = golden_o3["afterupdate_greens"]      # the reference applies update_greens!(mc,7) first (:185)
+    rng = JuliaMT(123456789)
+    st = UniformStream(np.array([rng.rand() for _ in range(64)]))
+    acc = mc.local_updates(st)
+    assert acc == 0.6875
+    assert st.consumed == 58
+    assert np.array_equal(mc.hsfield, golden_o3["afterlocal_hsfield"])
+    assert maxabs(mc.greens, golden_o3["afterlocal_greens"]) < 1e-12
+    assert np.isclose(mc.boson_action, 75.18407422927604, rtol=1e-12)
+    mc.close()
+
+
+@pytest.mark.parametrize("L,M,delay", [(4, 20, 0), (4, 20, 3), (8, 20, 0)])
+def test_sweep_vs_oracle_shared_stream(L, M, delay):
+    # same field + same uniform stream => identical accept/reject sequence, bit-exact field, G within 1e-10
+    from dqmc_b200 import UniformStream
+    mc, om = _mk(L, M, False, delay=delay)
+    rs = np.random.RandomState(5)
+    field = rs.rand(3, L * L, M)
+    u = rs.rand(4 * L * L * 2 * M)
+    mc.init(field)
+    om.init(field)
+    st, ost = UniformStream(u), OracleStream(u)
+    nacc_o = 0
+    for _ in range(2 * M):
+        om.propagate()
+        nacc_o += round(om.local_updates(ost) * L * L)
+    nacc, consumed = mc.sweep(st, nupdates=2 * M)
+    assert consumed == ost.pos and nacc == nacc_o
+    assert np.array_equal(mc.hsfield, om.hsfield)
+    assert maxabs(mc.greens, om.greens) < 1e-10
+    assert np.isclose(mc.boson_action, om.boson_action, rtol=1e-12)
+    assert (mc.current_slice, mc.direction) == (om.current_slice + 1, om.direction)
+    mc.close()
+
+
+# ------------------------------------------------------------------------------------------ BASELINE sizes: properties
+@pytest.mark.parametrize("L,M", [(12, 40), (16, 40)])
+def test_large_size_properties(L, M):
+    from dqmc_b200 import UniformStream
+    mc, _ = _mk(L, M, False)
+    n = mc.n
+    rs = np.random.RandomState(6)
+    field = rs.rand(3, L * L, M)
+    mc.hsfield = field
+    A = _rand_c(rs, n, n)
+    assert maxabs(mc.multiply_B_inv_left(7, mc.multiply_B_left(7, A)), A) < 1e-12
+    assert maxabs(mc.multiply_B_inv_right(7, mc.multiply_B_right(7, A)), A) < 1e-12
+    U, D, T = mc.decompose_udt(A * np.logspace(10, -30, n)[None, :])
+    assert maxabs(U.conj().T @ U, np.eye(n)) < 1e-12
+    mc.init(field)
+    g_first = mc.greens
+    st = UniformStream(rs.rand(4 * L * L * 2 * M))
+    nacc, consumed = mc.sweep(st, nupdates=2 * M)        # one up-down sweep ends on the measurement slice (M, -1)
+    assert (mc.current_slice, mc.direction) == (M, -1)
+    assert 0 < nacc < 2 * M * L * L
+    err, nonreal = mc.checks()
+    assert err < 1e-8 and nonreal == 0
+    # idempotence: with the field unchanged, a rebuilt stack gives back the propagated G
+    g_prop = mc.greens
+    h = mc.hsfield
+    mc.init(h)
+    assert maxabs(mc.greens, g_prop) < 1e-9
+    assert maxabs(g_first, g_prop) > 1e-6                 # the sweep did change the configuration
+    mc.close()
