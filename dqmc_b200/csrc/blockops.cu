@@ -149,8 +149,8 @@ int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, 
   const size_t smem = sizeof(cplx) * (size_t)nvec * ldx + tab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(apply_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(apply_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (set_max_dynamic_smem(apply_chain_kernel<false>, nullptr)) return -1;
+    if (set_max_dynamic_smem(apply_chain_kernel<true>, nullptr)) return -1;
     attr_done = true;
   }
   if (rows)

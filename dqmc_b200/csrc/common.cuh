@@ -48,6 +48,17 @@ enum { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };  // none, transpose, conj-trans
 extern char g_errbuf[512];
 extern long long g_launches;   // kernels launched by this library (all contexts)
 
+// Opt a kernel into the largest dynamic shared-memory size the device allows next to its static usage.
+template <typename K>
+static inline int set_max_dynamic_smem(K kernel, size_t* limit_out) {
+  cudaFuncAttributes fa;
+  CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+  const size_t lim = (size_t)227 * 1024 - fa.sharedSizeBytes;
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+  if (limit_out) *limit_out = lim;
+  return 0;
+}
+
 // FP64 tensor-core MMA (DMMA.8x8x4): D(8x8) += A(8x4,row) * B(4x8,col).
 // lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4], d0/d1 = D[lane/4][2*(lane%4) + {0,1}].
 DQMC_D void dmma884(double& d0, double& d1, double a, double b) {

@@ -304,11 +304,9 @@ int local_updates_grid(int n, int num_sms, int* rpc) {
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid) {
   const int ldk = 4 * a.kmax;
   const size_t smem = sizeof(cplx) * ((size_t)2 * a.rpc * ldk + 8 * ldk + 8 * a.rpc) + sizeof(double) * 3 * a.nsites;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(local_updates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static size_t smem_lim = 0;
+  if (smem_lim == 0 && set_max_dynamic_smem(local_updates_kernel, &smem_lim)) return -1;
+  if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "local_updates: shared memory %zu > %zu", smem, smem_lim); return -1; }
   LUArgs args = a;
   void* params[] = {&args};
   CUDA_TRY(cudaLaunchCooperativeKernel((const void*)local_updates_kernel, dim3(grid), dim3(256), params, smem, st));

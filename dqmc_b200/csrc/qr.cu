@@ -263,12 +263,9 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
 static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
   const int rs = (m + QR_CL - 1) / QR_CL;
   const size_t smem = sizeof(cplx) * ((size_t)QR_NB * rs + rs);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    smem_set = 200 * 1024;
-  }
-  if (smem > 200 * 1024) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
+  static size_t smem_lim = 0;
+  if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel, &smem_lim)) return -1;
+  if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
   qr_panel_kernel<<<QR_CL, 256, smem, st>>>(A, lda, m, nb, tau, dabs, T);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
@@ -429,12 +426,9 @@ int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy,
   g_launches++;
   const int n8 = (n + 7) / 8 * 8, lds = n8 + 4;
   const size_t smem = sizeof(cplx) * ((size_t)8 * lds + QR_NB * 8 + QR_NB * QR_NB);
-  if (smem > 227 * 1024) { snprintf(g_errbuf, sizeof(g_errbuf), "trsm: n=%d too large", n); return -1; }
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  static size_t smem_lim = 0;
+  if (smem_lim == 0 && set_max_dynamic_smem(trsm_kernel, &smem_lim)) return -1;
+  if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "trsm: n=%d too large", n); return -1; }
   trsm_kernel<<<(nrhs + 7) / 8, 256, smem, st>>>(A, lda, n, Y, ldy, nrhs, work, rowscale);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
