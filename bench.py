@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: sweeps/sec of the O(3) spin-fermion DQMC hot path (local updates + wrap + UDT stabilization)
+at L=16, beta=40 (n=1024, M=400, safe_mult=10), one independent Markov chain per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference (oracle port)
+
+One "step" = one sweep = M x { propagate; local_updates } incl. the K=M/safe_mult stabilizations of that
+direction = half a reference "udsweep" (dqmc_framework.jl:259-262).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "L16_beta40": dict(L=16, slices=400, safe_mult=10),   # BASELINE.json configs[3] (headline)
+    "L12_beta40": dict(L=12, slices=400, safe_mult=10),
+    "L8_beta20": dict(L=8, slices=200, safe_mult=10),
+    "L4_beta5": dict(L=4, slices=50, safe_mult=10),
+}
+MODEL = dict(hoppings="1.0,0.5,-0.5,-1.0", mu=-0.5, lam=0.5, r=2.0, c=3.0, u=1.0, delta_tau=0.1, box=0.5)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_inputs(cfg, chain, nsweeps):
+    """Documented counter-based generators: field seed 1234+chain, proposal stream seed 5678+chain."""
+    N, M = cfg["L"] ** 2, cfg["slices"]
+    field = np.random.Generator(np.random.Philox(1234 + chain)).random((M, N, 3)).T.copy(order="F")
+    u = np.random.Generator(np.random.Philox(5678 + chain)).random(4 * N * M * nsweeps)
+    return field, u
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_block_sample(cfg, nblocks=1):
+    """Time `nblocks` safe_mult blocks (safe_mult x {propagate; local_updates}, one stabilization each) of the oracle
+    port on the host cores at the workload's L, on a short chain (4 blocks) so setup stays bounded; scale to a sweep."""
+    import oracle
+    from oracle.dqmc import UniformStream
+    L, sm = cfg["L"], cfg["safe_mult"]
+    Mshort = 4 * sm
+    p = oracle.Params(L=L, slices=Mshort, safe_mult=sm, lam=MODEL["lam"], all_checks=False)
+    om = oracle.OracleDQMC(p)
+    rs = np.random.Generator(np.random.Philox(1234))
+    om.init(rs.random((Mshort, L * L, 3)).T.copy())
+    st = UniformStream(np.random.Generator(np.random.Philox(5678)).random(4 * L * L * sm * (nblocks + 1)))
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(nblocks * sm):
+        om.propagate()
+        acc += om.local_updates(st)
+    dt = time.perf_counter() - t0
+    blocks_per_sweep = cfg["slices"] // sm
+    return dt / nblocks * blocks_per_sweep, acc / (nblocks * sm)
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t_sweep, acc = cpu_block_sample(cfg, 1)
+        if it >= args.warmup:
+            times.append(t_sweep)
+    t = float(np.mean(times))
+    val = 1.0 / t
+    line = {"impl": "reference", "metric": "sweeps/sec", "value": val, "unit": "sweeps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": args.config, "note": "CPU restatement of the reference path (NumPy/SciPy, OpenBLAS)"},
+            "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port",
+                             "sample": "each step = 1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) "
+                                       "at the workload's L on a 4-block chain, scaled to a full sweep" % (cfg["slices"] // cfg["safe_mult"])},
+            "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_rooflines(mc, cfg, hbm_gbs, peak_src):
+    """Per-kernel roofline from CUDA-event timings inside the library (dqmc_bench_kernel)."""
+    n, N, sm = mc.n, cfg["L"] ** 2, cfg["safe_mult"]
+    out = {}
+    t_cublas = mc.bench_kernel(2, 5)
+    f64_peak = 8.0 * n ** 3 / (t_cublas * 1e-3) / 1e12          # measured cuBLAS ZGEMM ceiling, TFLOP/s
+    out["fp64_peak_tflops_cublas_zgemm"] = f64_peak
+    t = mc.bench_kernel(6, 20)
+    out["copy_G"] = {"ms": t, "GB/s": 32.0 * n * n / (t * 1e-3) / 1e9}
+    t = mc.bench_kernel(0, 20)
+    out["wrap"] = {"bound": "hbm", "ms": t, "achieved": 64.0 * n * n / (t * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                   "algorithmic_bytes": 64.0 * n * n}
+    t = mc.bench_kernel(7, 10)
+    out["b_chain"] = {"bound": "hbm", "ms": t, "achieved": 32.0 * n * n / (t * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                      "algorithmic_bytes": 32.0 * n * n, "flops": sm * 128.0 * n * n}
+    t = mc.bench_kernel(1, 10)
+    out["zgemm"] = {"bound": "tensor", "ms": t, "achieved": 8.0 * n ** 3 / (t * 1e-3) / 1e12, "peak": f64_peak, "unit": "TFLOP/s"}
+    t = mc.bench_kernel(3, 5)
+    out["udt"] = {"bound": "tensor", "ms": t, "achieved": 10.67 * n ** 3 / (t * 1e-3) / 1e12, "peak": f64_peak, "unit": "TFLOP/s",
+                  "algorithmic_flops": 10.67 * n ** 3}
+    t = mc.bench_kernel(4, 5)
+    # two GEMMs + QR (5.33) + apply Q^H to the rhs (8) + triangular solve (4) + final GEMM
+    fl = (3 * 8 + 5.33 + 8 + 4) * n ** 3
+    out["calculate_greens"] = {"bound": "tensor", "ms": t, "achieved": fl / (t * 1e-3) / 1e12, "peak": f64_peak, "unit": "TFLOP/s",
+                               "algorithmic_flops": fl}
+    t = mc.bench_kernel(5, 3)
+    out["local_updates_slice"] = {"ms": t, "us_per_proposal": t * 1e3 / N}
+    for k, v in out.items():
+        if isinstance(v, dict) and "achieved" in v:
+            v["frac"] = v["achieved"] / v["peak"]
+            v["peak_source"] = peak_src if v["bound"] == "hbm" else "cuBLAS ZGEMM measured in this run"
+    return out
+
+
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch
+    from dqmc_b200 import DQMC, Params, UniformStream
+    from dqmc_b200 import parallel
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        parallel.init_process_group("nccl")
+    L, M, sm = cfg["L"], cfg["slices"], cfg["safe_mult"]
+    N = L * L
+    p = Params(L=L, slices=M, safe_mult=sm, delta_tau=MODEL["delta_tau"], lambda_=MODEL["lam"], r=MODEL["r"], c=MODEL["c"],
+               u=MODEL["u"], mu1=MODEL["mu"], mu2=MODEL["mu"], hoppings=MODEL["hoppings"], box=MODEL["box"],
+               Bfield=False, all_checks=bool(args.all_checks))
+    mc = DQMC(p, device=local_rank, delay=args.delay)
+    nsw = args.warmup + args.steps
+    field, u = synthetic_inputs(cfg, rank, nsw)
+    mc.init(field)
+
+    # ---- device-resident arm: uniforms already in HBM, timed with CUDA events on the library's stream
+    mc.set_uniforms(u)
+    for _ in range(args.warmup):
+        mc.sweep(None)
+    mc.set_timing(True)
+    mc.timers()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        torch.distributed.barrier()
+    mc.sync()
+    sampler.start()
+    launches0 = mc.kernel_launches()
+    t0 = time.perf_counter()
+    nacc = 0
+    for _ in range(args.steps):
+        a, _c = mc.sweep(None)
+        nacc += a
+    mc.sync()
+    wall = time.perf_counter() - t0
+    launches = mc.kernel_launches() - launches0
+    tm = mc.timers()
+    clocks = sampler.stop()
+    mc.set_timing(False)
+    t_dev = tm["sweep"] * 1e-3                       # CUDA-event time of the K sweeps
+    if world > 1:
+        tt = torch.tensor([t_dev, wall], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        t_dev, wall = tt.tolist()
+    value = world * args.steps / t_dev
+
+    # ---- end-to-end arm: host uniforms in (pinned), configuration + counters out, every sweep, wall clock
+    nsw_e = args.steps
+    field_e, u_e = synthetic_inputs(cfg, 1000 + rank, nsw_e)
+    upin = torch.empty(4 * N * M, dtype=torch.float64, pin_memory=True).numpy()
+    if world > 1:
+        torch.distributed.barrier()
+    mc.sync()
+    t0 = time.perf_counter()
+    for k in range(nsw_e):
+        upin[:] = u_e[k * 4 * N * M:(k + 1) * 4 * N * M]
+        mc.sweep(UniformStream(upin))
+        _conf = mc.hsfield
+    mc.sync()
+    wall_e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([wall_e], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        wall_e = tt.item()
+    e2e = world * nsw_e / wall_e
+
+    # ---- pooled measurement bins across chains (the path's only collective; outside the timed region)
+    h = mc.hsfield
+    phi2 = np.einsum("kis,kis->is", h, h).ravel()
+    pooled_mean, pooled_var = parallel.combined_mean_and_var(phi2.size, np.array([phi2.mean()]), np.array([phi2.var(ddof=1)]))
+    err, nonreal = mc.checks()
+
+    if rank == 0:
+        hbm_gbs, peak_src = measured_peaks()
+        kr = kernel_rooflines(mc, cfg, hbm_gbs, peak_src)
+        phases = {k: tm[k] / args.steps for k in ("wrap", "local_updates", "stack_udt", "calculate_greens")}
+        # sweep-level roofline: algorithmic FP64 flops at the measured cuBLAS ZGEMM ceiling + wrap bytes at HBM peak
+        n = mc.n
+        acc_rate = nacc / (args.steps * M * N)
+        f_sweep = acc_rate * M * N * 32.0 * n * n + (M // sm) * 107.3 * n ** 3
+        b_sweep = M * 64.0 * n * n
+        f64_peak = kr["fp64_peak_tflops_cublas_zgemm"]
+        t_roof = f_sweep / (f64_peak * 1e12) + b_sweep / (hbm_gbs * 1e9)
+        dom = max(phases, key=phases.get)
+        dom_map = {"wrap": "wrap", "stack_udt": "udt", "calculate_greens": "calculate_greens", "local_updates": None}
+        if dom_map[dom] is not None:
+            rf = dict(kr[dom_map[dom]])
+            roof = {"kernel": dom_map[dom], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": rf["unit"],
+                    "frac": rf["frac"], "traffic": None, "peak_source": rf["peak_source"]}
+        else:
+            # local updates: FP64 work = rank-4 Woodbury updates (32 n^2 flops per accepted proposal, flushed as GEMMs)
+            t_lu = phases["local_updates"] * 1e-3
+            ach = acc_rate * M * N * 32.0 * n * n / t_lu / 1e12
+            roof = {"kernel": "local_updates_kernel", "bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
+                    "frac": ach / f64_peak, "traffic": None, "peak_source": "cuBLAS ZGEMM measured in this run",
+                    "serial_floor_us_per_proposal": kr["local_updates_slice"]["us_per_proposal"]}
+        t_cpu, acc_cpu = cpu_block_sample(cfg, 1)
+        line = {"metric": "sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+                "config": {"workload": args.config, "model": "O(3) spin-fermion, square lattice, Assaad checkerboard, B-field off",
+                           "L": L, "beta": M * MODEL["delta_tau"], "slices": M, "safe_mult": sm, "n": n, "delay": mc_delay(args),
+                           "acceptance": acc_rate, "chains": world, "parallelism": f"{world} independent chains (replicas only)",
+                           "l2": "no flush: each sweep streams the 1.3 GB UDT stack (>> 126 MB L2); G (16 MB) is L2-resident by design"},
+                "e2e": {"value": e2e, "unit": "sweeps/s", "h2d_bytes_per_step": 8 * 4 * N * M, "d2h_bytes_per_step": 8 * 3 * N * M + 24},
+                "gpu_launches": launches, "clocks": clocks, "wall_ms_per_step": wall / args.steps * 1e3,
+                "roofline": roof,
+                "sweep_roofline": {"flops": f_sweep, "bytes": b_sweep, "t_roofline_ms": t_roof * 1e3, "frac": t_roof / (t_dev / args.steps),
+                                   "fp64_peak_tflops": f64_peak, "hbm_gbs": hbm_gbs},
+                "phases_ms_per_sweep": phases, "kernels": kr,
+                "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) at L=%d on a "
+                                           "4-block chain, scaled to a full sweep; oracle port, NumPy/SciPy + OpenBLAS, all host cores"
+                                           % (M // sm, L), "acceptance": acc_cpu},
+                "checks": {"max_propagation_error": err, "nonreal_detratios": nonreal,
+                           "pooled_phi2_mean": float(pooled_mean[0]), "pooled_phi2_var": float(pooled_var[0])}}
+        print(json.dumps(line))
+    mc.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def mc_delay(args):
+    return args.delay if args.delay > 0 else 16
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="L16_beta40", choices=sorted(CONFIGS))
+    ap.add_argument("--delay", type=int, default=0)
+    ap.add_argument("--all-checks", type=int, default=1)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+    else:
+        run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,8 @@ Random numbers are *injected*: ``local_updates`` takes any object with a ``rand(
 """
 import numpy as np
 import scipy.linalg as sla
+from scipy.linalg import blas
+import scipy.sparse as sp
 
 from .model import build_model
 
@@ -105,7 +107,7 @@ class OracleDQMC:
 
     # ---------------------------------------------------------------- interactions.jl
     def interaction_matrix_exp(self, slc, power=1.0):
-        """interactions.jl:35-88: dense n x n e^{-power dtau V(slice)} (block-sparse in the reference)."""
+        """interactions.jl:35-88: sparse n x n e^{-power dtau V(slice)} (10 diagonal N-blocks, 3 nnz per row)."""
         p, N = self.p, self.N
         assert p.opdim == 3
         hs = self.hsfield[:, :, slc]
@@ -114,16 +116,13 @@ class OracleDQMC:
         C = np.cosh(p.lam * p.delta_tau * nrm).astype(complex)
         S = (1j * hs[1] - hs[0]) * power * sh
         R = (-hs[2]) * power * sh + 0j
-        eV = np.zeros((self.n, self.n), dtype=complex)
         idx = np.arange(N)
-
-        def blk(r, c, v):
-            eV[r * N + idx, c * N + idx] = v
-
-        blk(0, 0, C); blk(0, 1, S); blk(1, 0, np.conj(S)); blk(1, 1, C)
-        blk(0, 3, R); blk(1, 2, -R); blk(2, 1, -R); blk(2, 2, C); blk(2, 3, np.conj(S))
-        blk(3, 0, R); blk(3, 2, S); blk(3, 3, C)
-        return eV
+        blocks = [(0, 0, C), (0, 1, S), (1, 0, np.conj(S)), (1, 1, C), (0, 3, R), (1, 2, -R), (2, 1, -R), (2, 2, C),
+                  (2, 3, np.conj(S)), (3, 0, R), (3, 2, S), (3, 3, C)]
+        rows = np.concatenate([r * N + idx for r, _, _ in blocks])
+        cols = np.concatenate([c * N + idx for _, c, _ in blocks])
+        vals = np.concatenate([v for _, _, v in blocks])
+        return sp.csc_matrix((vals, (rows, cols)), shape=(self.n, self.n))
 
     def interaction_matrix_exp_op(self, op, power=1.0):
         """interactions.jl:102-141 (4x4, O(3))."""
@@ -158,7 +157,7 @@ class OracleDQMC:
         M = (l.chkr_hop[0].T @ M.T).T
         M = (l.chkr_hop_half[1].T @ M.T).T
         M = (l.chkr_mu.T @ M.T).T
-        M = M @ eV
+        M = (eV.T @ M.T).T
         return M
 
     def multiply_B_inv_left(self, slc, M):
@@ -176,7 +175,7 @@ class OracleDQMC:
         """slice_matrices.jl:179-201: M <- M e^{+dtau V} mu^-1 hopB½^-1 hopA^-1 hopB½^-1."""
         l = self.l
         eV = self.interaction_matrix_exp(slc, -1.0)
-        M = M @ eV
+        M = (eV.T @ M.T).T
         M = (l.chkr_mu_inv.T @ M.T).T
         M = (l.chkr_hop_half_inv[1].T @ M.T).T
         M = (l.chkr_hop_inv[0].T @ M.T).T
@@ -371,15 +370,18 @@ class OracleDQMC:
         return complex(np.linalg.det(self.Mmat))
 
     def update_greens(self, i):
-        """local_updates.jl:61-95: G += (G[:,i::N]-E_i) M^-1 . delta_i G[i::N,:]."""
+        """local_updates.jl:61-95: G += (G[:,i::N]-E_i) M^-1 . delta_i G[i::N,:]  (in-place zgemm like mul!/axpy)."""
         N = self.N
+        if not self.greens.flags.f_contiguous:
+            self.greens = np.asfortranarray(self.greens)
         g = self.greens
         A = g[:, i::N].copy()
         for k in range(4):
             A[i + k * N, k] -= 1.0
         A = A @ np.linalg.inv(self.Mmat)
         B = self.delta_i @ g[i::N, :]
-        g += A @ B
+        out = blas.zgemm(1.0, A, B, beta=1.0, c=g, overwrite_c=1)
+        assert out is g or np.shares_memory(out, g)
 
     def local_updates(self, rng):
         """local_updates.jl:1-39.  Returns the acceptance fraction."""

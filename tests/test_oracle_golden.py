@@ -122,8 +122,8 @@ def test_interactions(mc_b, mc_nob, golden_o3):
     # with the seeded start field of init!(mc) (found by trying both; slice 3 either way).
     for mc, pre, h in ((mc_nob, "nob_", golden_o3["randconf"]), (mc_b, "", seeded_field())):
         mc.hsfield = h.copy()
-        assert maxabs(mc.interaction_matrix_exp(2, 1.0), csc_dense(golden_o3, pre + "eVplus")) < 1e-15
-        assert maxabs(mc.interaction_matrix_exp(2, -1.0), csc_dense(golden_o3, pre + "eVminus")) < 1e-15
+        assert maxabs(mc.interaction_matrix_exp(2, 1.0).toarray(), csc_dense(golden_o3, pre + "eVplus")) < 1e-15
+        assert maxabs(mc.interaction_matrix_exp(2, -1.0).toarray(), csc_dense(golden_o3, pre + "eVminus")) < 1e-15
         ev = mc.interaction_matrix_exp_op(np.array([0.130018, 0.792039, 0.683411]), 1.0)
         assert maxabs(ev, golden_o3[pre + "eVexpop"]) < 1e-15
 
