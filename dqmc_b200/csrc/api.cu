@@ -177,8 +177,11 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->hs, (size_t)3 * c->N * c->M));
   TRY(c, dmalloc(c, &c->hs_bak, (size_t)3 * c->N * c->M));
   TRY(c, dmalloc(c, &c->nbr, (size_t)4 * c->N));
-  TRY(c, dmalloc(c, &c->At, (size_t)4 * c->kmax * n));
-  TRY(c, dmalloc(c, &c->Bm, (size_t)4 * c->kmax * n));
+  // two buffers each (double-buffered by flush batch), pre-filled with the all-ones NaN sentinel the kernel spins on
+  CU(c, cudaMalloc((void**)&c->At, sizeof(cplx) * 2 * 4 * c->kmax * n));
+  CU(c, cudaMalloc((void**)&c->Bm, sizeof(cplx) * 2 * 4 * c->kmax * n));
+  CU(c, cudaMemsetAsync(c->At, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
+  CU(c, cudaMemsetAsync(c->Bm, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
   c->unif = nullptr; c->unif_cap = c->unif_n = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));

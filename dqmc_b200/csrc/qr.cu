@@ -4,12 +4,14 @@ namespace cg = cooperative_groups;
 
 // =====================================================================================================
 // Panel factorization: one thread-block cluster of QR_CL CTAs; each CTA keeps a slab of rows of the
-// m x nb panel in shared memory.  Per column ONE cluster barrier: every CTA publishes the partial dot
-// products of the current column with all other panel columns (rows below the diagonal only) in its own
-// shared memory, the others pull them through distributed shared memory.  From those sums every CTA
-// derives beta, tau, v and the update coefficients redundantly, so no second exchange is needed; the
-// dots with the already-finished columns give V^H v_j, i.e. the compact-WY T factor for free.
+// m x nb panel in shared memory (row-major, 32 columns per row, padded to 33).  Thread (c, g) owns column c
+// on the rows {g, g+8, ...} of the slab.  Per column ONE cluster barrier: every CTA reduces the dot products
+// of the current column with all other panel columns over its rows (rows below the diagonal only) and pushes
+// them, plus row j if it owns it, into every CTA's shared memory (distributed shared memory stores).  After the
+// barrier every CTA derives beta, tau, v and the update coefficients redundantly from local data.  The dots with
+// the already-finished columns give V^H v_j, i.e. the compact-WY T factor, for free.
 // =====================================================================================================
+#define QR_LDA 33
 __global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(256)
 qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
                 double* __restrict__ dabs_out, cplx* __restrict__ Tout) {
@@ -18,59 +20,67 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
   const int rs = (m + QR_CL - 1) / QR_CL;
   const int r_begin = rank * rs;
   const int nloc = max(0, min(m, r_begin + rs) - r_begin);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, g = tid >> 5, c = tid & 31;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // a[c*rs + rloc]
-  cplx* vloc = a + (size_t)QR_NB * rs;           // [rs]
-  __shared__ cplx xch[2][QR_NB];                 // my partial dots, double-buffered by column parity
-  __shared__ cplx rowv[2][QR_NB];                // row j of the panel (owner CTA only)
-  __shared__ cplx Ptot[QR_NB], rowj[QR_NB], wv[QR_NB];
+  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // a[rl*QR_LDA + c]
+  __shared__ cplx part[8][QR_NB];                // per-warp partial dots
+  __shared__ cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][column]: partial dots of every CTA
+  __shared__ cplx rowv[2][QR_NB];                // [parity][column]: row j of the panel (pushed by its owner)
   __shared__ cplx Tsm[QR_NB][QR_NB + 1];
   __shared__ cplx gsm[QR_NB];
+  __shared__ cplx tpart[8][QR_NB];
   __shared__ cplx tau_s[QR_NB];
   __shared__ double beta_s[QR_NB];
 
-  for (int c = 0; c < nb; ++c)
-    for (int r = tid; r < nloc; r += blockDim.x) a[c * rs + r] = A[(size_t)c * lda + r_begin + r];
+  // global -> shared: consecutive threads along rows (coalesced), 32 columns
+  for (int e = tid; e < nloc * QR_NB; e += blockDim.x) {
+    const int rl = e % nloc, cc = e / nloc;
+    a[rl * QR_LDA + cc] = cc < nb ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
+  }
   if (rank == 0)
     for (int e = tid; e < QR_NB * (QR_NB + 1); e += blockDim.x) (&Tsm[0][0])[e] = cmake(0.0, 0.0);
   __syncthreads();
 
   for (int j = 0; j < nb; ++j) {
     const int par = j & 1;
-    // ---- phase A: partial dots over my rows r > j
-    for (int cc = warp; cc < nb; cc += 8) {
-      cplx acc = cmake(0.0, 0.0);
-      for (int rl = lane; rl < nloc; rl += 32) {
-        if (r_begin + rl > j) {
-          if (cc >= j) cfma_conj(acc, a[j * rs + rl], a[cc * rs + rl]);
-          else cfma_conj(acc, a[cc * rs + rl], a[j * rs + rl]);
-        }
+    // ---- phase A: t_c = sum_{r>j} conj(a[r][j]) a[r][c] over my rows (4 independent accumulators)
+    {
+      cplx acc0 = cmake(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+      int rl = g;
+      // rows are visited in increasing order; skip those with r <= j
+      const int first = j + 1 - r_begin;                    // first local row with r > j
+      if (first > rl) rl += ((first - rl + 7) / 8) * 8;
+      for (; rl + 24 < nloc; rl += 32) {
+        cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
+        cfma_conj(acc1, a[(rl + 8) * QR_LDA + j], a[(rl + 8) * QR_LDA + c]);
+        cfma_conj(acc2, a[(rl + 16) * QR_LDA + j], a[(rl + 16) * QR_LDA + c]);
+        cfma_conj(acc3, a[(rl + 24) * QR_LDA + j], a[(rl + 24) * QR_LDA + c]);
       }
-      acc.x = warp_sum(acc.x);
-      acc.y = warp_sum(acc.y);
-      if (lane == 0) xch[par][cc] = acc;
-    }
-    const int owner = j / rs;
-    if (rank == owner && tid < nb) rowv[par][tid] = a[tid * rs + (j - r_begin)];
-    cl.sync();
-    // ---- phase B: pull the partials of all CTAs
-    if (tid < nb) {
-      cplx tot = cmake(0.0, 0.0);
-#pragma unroll
-      for (int src = 0; src < QR_CL; ++src) {
-        const cplx* rx = cl.map_shared_rank(&xch[0][0], src);
-        tot = cadd(tot, rx[par * QR_NB + tid]);
-      }
-      Ptot[tid] = tot;
-      const cplx* rr = cl.map_shared_rank(&rowv[0][0], owner);
-      rowj[tid] = rr[par * QR_NB + tid];
+      for (; rl < nloc; rl += 8) cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
+      part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
     }
     __syncthreads();
-    // ---- phase C: reflector parameters (every thread, redundantly)
-    const cplx alpha = rowj[j];
-    const double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + Ptot[j].x);
+    {
+      // every warp g sums the 8 partials of column c and pushes the result to CTA g of the cluster
+      cplx t = part[0][c];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t = cadd(t, part[w][c]);
+      cplx* dst = cl.map_shared_rank(&xch[0][0][0], g);
+      dst[(par * QR_CL + rank) * QR_NB + c] = t;
+      const int owner = j / rs;
+      if (rank == owner) {
+        cplx* dr = cl.map_shared_rank(&rowv[0][0], g);
+        dr[par * QR_NB + c] = a[(j - r_begin) * QR_LDA + c];
+      }
+    }
+    cl.sync();
+    // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
+    cplx tc = xch[par][0][c], tj = xch[par][0][j];
+#pragma unroll
+    for (int src = 1; src < QR_CL; ++src) { tc = cadd(tc, xch[par][src][c]); tj = cadd(tj, xch[par][src][j]); }
+    const cplx alpha = rowv[par][j], rowc = rowv[par][c];
+    const double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + tj.x);
     double beta;
     cplx tau, scale;
     if (nrm == 0.0) {
@@ -80,51 +90,59 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       tau = cmake((beta - alpha.x) / beta, -alpha.y / beta);
       scale = cdiv(cmake(1.0, 0.0), cmake(alpha.x - beta, alpha.y));
     }
-    const cplx ctau = cconj(tau);
-    for (int rl = tid; rl < nloc; rl += blockDim.x) {
-      int r = r_begin + rl;
-      vloc[rl] = r > j ? cmul(a[j * rs + rl], scale) : (r == j ? cmake(1.0, 0.0) : cmake(0.0, 0.0));
+    // w_c = conj(tau) * v^H a_c = conj(tau) * (a[j][c] + conj(scale) * t_c)      (c > j)
+    cplx wc = rowc;
+    cfma(wc, cconj(scale), tc);
+    wc = cmul(cconj(tau), wc);
+    if (rank == 0 && g == 0) {
+      // g_c = V_c^H v_j = conj(V[j][c]) + scale * conj(t_c)   (c < j)
+      cplx gg = cconj(rowc);
+      cfma(gg, scale, cconj(tc));
+      gsm[c] = c < j ? gg : cmake(0.0, 0.0);
+      if (c == 0) { tau_s[j] = tau; beta_s[j] = beta; }
     }
-    if (tid > j && tid < nb) {   // w_cc = v^H a_cc = a[j][cc] + conj(scale) * sum_{r>j} conj(x_r) a[r][cc]
-      cplx w = rowj[tid];
-      cfma(w, cconj(scale), Ptot[tid]);
-      wv[tid] = cmul(ctau, w);
-    }
-    if (rank == 0 && tid < j) {  // g = V^H v_j = conj(V[j][t]) + scale * sum_{r>j} conj(V[r][t]) x_r
-      cplx g = cconj(rowj[tid]);
-      cfma(g, scale, Ptot[tid]);
-      gsm[tid] = g;
-    }
-    if (tid == 0) { tau_s[j] = tau; beta_s[j] = beta; }
-    __syncthreads();
-    // ---- phase D: a_cc -= conj(tau) w_cc v  (rows r >= j), store v and beta in column j
-    const int ncol = nb - j - 1;
-    for (int e = tid; e < ncol * nloc; e += blockDim.x) {
-      int cc = j + 1 + e / nloc, rl = e % nloc;
-      if (r_begin + rl >= j) {
-        cplx t = a[cc * rs + rl];
-        cplx p = cmul(vloc[rl], wv[cc]);
-        a[cc * rs + rl] = csub(t, p);
+    // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j); column j <- v (below the diagonal) and beta (diagonal)
+    {
+      int rl = g;
+      const int first = j - r_begin;                        // first local row with r >= j
+      if (first > rl) rl += ((first - rl + 7) / 8) * 8;
+      for (; rl < nloc; rl += 8) {
+        const int r = r_begin + rl;
+        const cplx xj = a[rl * QR_LDA + j];
+        const cplx v = r == j ? cmake(1.0, 0.0) : cmul(xj, scale);
+        cplx t = a[rl * QR_LDA + c];
+        __syncwarp();
+        if (c > j) t = csub(t, cmul(v, wc));
+        else if (c == j) t = r == j ? cmake(beta, 0.0) : v;
+        a[rl * QR_LDA + c] = t;
       }
     }
-    for (int rl = tid; rl < nloc; rl += blockDim.x) {
-      int r = r_begin + rl;
-      if (r > j) a[j * rs + rl] = vloc[rl];
-      else if (r == j) a[j * rs + rl] = cmake(beta, 0.0);
-    }
-    if (rank == 0 && warp == 7) {  // T(0:j,j) = -tau * T(0:j,0:j) * g ; T(j,j) = tau   (zlarft, forward/columnwise)
-      if (lane < j) {
-        cplx acc = cmake(0.0, 0.0);
-        for (int k = lane; k < j; ++k) cfma(acc, Tsm[lane][k], gsm[k]);
-        Tsm[lane][j] = cneg(cmul(tau, acc));
+    if (rank == 0) {
+      // T(0:j,j) = -tau * T(0:j,0:j) * g ; T(j,j) = tau   (zlarft, forward/columnwise); thread (i=c, k = g mod 8)
+      __syncthreads();
+      cplx acc = cmake(0.0, 0.0);
+      if (c < j)
+        for (int k = c + ((g - c) & 7); k < j; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
+      tpart[g][c] = acc;
+      __syncthreads();
+      if (g == 0) {
+        if (c < j) {
+          cplx t = tpart[0][c];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) t = cadd(t, tpart[w][c]);
+          Tsm[c][j] = cneg(cmul(tau, t));
+        } else if (c == j) {
+          Tsm[j][j] = tau;
+        }
       }
-      if (lane == 0) Tsm[j][j] = tau;
     }
     __syncthreads();
   }
 
-  for (int c = 0; c < nb; ++c)
-    for (int r = tid; r < nloc; r += blockDim.x) A[(size_t)c * lda + r_begin + r] = a[c * rs + r];
+  for (int e = tid; e < nloc * nb; e += blockDim.x) {
+    const int rl = e % nloc, cc = e / nloc;
+    A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
+  }
   if (rank == 0) {
     for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) {
       int i = e % QR_NB, k = e / QR_NB;
@@ -132,7 +150,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     }
     if (tid < nb) { tau_out[tid] = tau_s[tid]; dabs_out[tid] = fabs(beta_s[tid]); }
   }
-  cl.sync();  // no CTA may exit while others may still read its shared memory
+  cl.sync();  // no CTA may exit while others may still write into its shared memory
 }
 
 // =====================================================================================================
@@ -262,7 +280,7 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
 
 static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
   const int rs = (m + QR_CL - 1) / QR_CL;
-  const size_t smem = sizeof(cplx) * ((size_t)QR_NB * rs + rs);
+  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * rs + 8);
   static size_t smem_lim = 0;
   if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
