@@ -59,6 +59,8 @@ struct dqmc_ctx {
   double* d_dS;
   int* d_flags;
   unsigned int* d_bar;
+  long long* d_prof;
+  bool lu_prof;
   double* d_logdet;
   double* d_check;     // [0] running max, [1] scratch
   bool have_nbr, ops_ready;
@@ -185,6 +187,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   c->unif = nullptr; c->unif_cap = c->unif_n = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
+  TRY(c, dmalloc(c, &c->d_prof, 16)); c->lu_prof = false;
   TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
@@ -731,7 +734,7 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   a.inv_dtau_c2 = 1.0 / (c->p.delta_tau * c->p.c * c->p.c); a.r = c->p.r; a.u = c->p.u;
   a.G = c->G; a.At = c->At; a.Bm = c->Bm; a.hs = c->hs; a.nbr = c->nbr;
   a.unif = c->unif; a.nunif = c->unif_n; a.pos = c->d_pos; a.accepted = c->d_acc; a.dS = c->d_dS;
-  a.flags = c->d_flags; a.bar = c->d_bar;
+  a.flags = c->d_flags; a.bar = c->d_bar; a.prof = c->lu_prof ? c->d_prof : nullptr;
   TRY(c, launch_local_updates(c->st, a, c->lu_grid));
   return 0;
 }
@@ -793,6 +796,17 @@ extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {
 
 extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t enable) {
   c->timing = enable != 0;
+  return 0;
+}
+
+// debug hook: cycle counters of the last local_updates launch (CTA 0); enable with enable != 0
+extern "C" int dqmc_lu_profile(dqmc_ctx* c, int32_t enable, int64_t* out16) {
+  CU(c, cudaSetDevice(c->p.device));
+  c->lu_prof = enable != 0;
+  if (out16) {
+    CU(c, cudaMemcpyAsync(out16, c->d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+  }
   return 0;
 }
 

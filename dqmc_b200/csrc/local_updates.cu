@@ -161,7 +161,14 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   long long nacc = 0;
   double dS_sum = 0.0;
   int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0;
+  // optional cycle profile of CTA 0: arrival stamps before the two CTA barriers of an iteration (a clock read right
+  // after bar.sync would capture the barrier's issue, not its release)
+  const bool prof = (a.prof != nullptr) && blockIdx.x == 0;
+  __shared__ long long stampA[8], stampB[8];
+  long long p_role[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
   __syncthreads();
+  const long long t_begin = clock64();
+  rel_prev = t_begin;
 
   // G-derived data of `site` into buffer bb (all threads of the CTA or the 128 prefetch threads; tp = local index)
   auto fetch_G = [&](int site, int bb, int tp, int nth) {
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         if (q == 0) g4e[nb][o] = cadd(g4r[o], acc);
       }
     }
+    if (prof && lane == 0) stampA[warp] = clock64();
     __syncthreads();
     const int accepted = s_accept, scn = s_scn;
     pos += (scn == 1) ? 3 : 4;
@@ -333,7 +341,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       np += 4;
     }
     // ================= flush: G += A B over the pending 4*kc columns =================
-    if (kc == a.kmax || (i == N - 1 && kc > 0)) {
+    const bool do_flush = (kc == a.kmax || (i == N - 1 && kc > 0));
+    if (do_flush) {
+      n_fl++;
       grid_barrier(a.bar, gridDim.x);
       const int K = 4 * kc;
       const int lo = lane >> 2, lk = lane & 3;
@@ -408,7 +418,22 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       }
     }
     s_cur = scn;
+    if (prof && lane == 0) stampB[warp] = clock64();
     __syncthreads();
+    if (prof && tid == 0) {
+      long long relA = stampA[0], relB = stampB[0];
+      for (int w = 0; w < 8; ++w) { relA = max(relA, stampA[w]); relB = max(relB, stampB[w]); p_role[w] += stampA[w] - rel_prev; }
+      p_s1 += relA - rel_prev;
+      if (do_flush) p_flush += relB - relA; else if (accepted) p_rest_acc += relB - relA; else p_rest_rej += relB - relA;
+      rel_prev = relB;
+    }
+  }
+  if (prof && tid == 0) {
+    // [0] total, [1] stage 1, [2] stage 2 of accepted sites (no flush), [3] iterations with a flush (stage 2 + flush),
+    // [4] #flushes, [5] accepts, [6] stage 2 of rejected sites, [8+w] stage-1 role time of warp w
+    a.prof[0] = clock64() - t_begin; a.prof[1] = p_s1; a.prof[2] = p_rest_acc; a.prof[3] = p_flush; a.prof[4] = n_fl;
+    a.prof[5] = nacc; a.prof[6] = p_rest_rej;
+    for (int w = 0; w < 8; ++w) a.prof[8 + w] = p_role[w];
   }
 
   if (blockIdx.x == 0 && tid == 0) {

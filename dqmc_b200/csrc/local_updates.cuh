@@ -22,6 +22,7 @@ struct LUArgs {
   double* dS;                      // in/out: accumulated -log(exp(-dS)) of accepted proposals
   int* flags;                      // [0] stream exhausted, [1] non-real determinant ratios seen
   unsigned int* bar;               // grid barrier state {count, generation}
+  long long* prof;                 // optional [16] cycle counters of CTA 0 (nullptr = off)
 };
 
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid);

@@ -60,6 +60,15 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       for (; rl < nloc; rl += 8) cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
       part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
     }
+    if (rank == 0 && j > 0) {
+      // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise), computed
+      // in the shadow of this column's dot products; thread (i = c, k = g mod 8)
+      const int jp = j - 1;
+      cplx acc = cmake(0.0, 0.0);
+      if (c < jp)
+        for (int k = c + ((g - c) & 7); k < jp; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
+      tpart[g][c] = acc;
+    }
     __syncthreads();
     {
       // every warp g sums the 8 partials of column c and pushes the result to CTA g of the cluster
@@ -72,6 +81,17 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       if (rank == owner) {
         cplx* dr = cl.map_shared_rank(&rowv[0][0], g);
         dr[par * QR_NB + c] = a[(j - r_begin) * QR_LDA + c];
+      }
+      if (rank == 0 && j > 0 && g == 1) {
+        const int jp = j - 1;
+        if (c < jp) {
+          cplx tt = tpart[0][c];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) tt = cadd(tt, tpart[w][c]);
+          Tsm[c][jp] = cneg(cmul(tau_s[jp], tt));
+        } else if (c == jp) {
+          Tsm[jp][jp] = tau_s[jp];
+        }
       }
     }
     cl.sync();
@@ -87,8 +107,10 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       beta = 0.0; tau = cmake(0.0, 0.0); scale = cmake(0.0, 0.0);
     } else {
       beta = alpha.x >= 0.0 ? -nrm : nrm;
-      tau = cmake((beta - alpha.x) / beta, -alpha.y / beta);
-      scale = cdiv(cmake(1.0, 0.0), cmake(alpha.x - beta, alpha.y));
+      const double ib = 1.0 / beta;
+      tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
+      const double ar = alpha.x - beta, id = 1.0 / (ar * ar + alpha.y * alpha.y);
+      scale = cmake(ar * id, -alpha.y * id);
     }
     // w_c = conj(tau) * v^H a_c = conj(tau) * (a[j][c] + conj(scale) * t_c)      (c > j)
     cplx wc = rowc;
@@ -103,37 +125,51 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     }
     // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j); column j <- v (below the diagonal) and beta (diagonal)
     {
-      int rl = g;
+      int rl0 = g;
       const int first = j - r_begin;                        // first local row with r >= j
-      if (first > rl) rl += ((first - rl + 7) / 8) * 8;
-      for (; rl < nloc; rl += 8) {
+      if (first > rl0) rl0 += ((first - rl0 + 7) / 8) * 8;
+      if (c > j) {
+        int rl = rl0;
+        for (; rl + 24 < nloc; rl += 32) {
+          cplx x0 = a[rl * QR_LDA + j], x1 = a[(rl + 8) * QR_LDA + j], x2 = a[(rl + 16) * QR_LDA + j], x3 = a[(rl + 24) * QR_LDA + j];
+          cplx t0 = a[rl * QR_LDA + c], t1 = a[(rl + 8) * QR_LDA + c], t2 = a[(rl + 16) * QR_LDA + c], t3 = a[(rl + 24) * QR_LDA + c];
+          x0 = (r_begin + rl == j) ? cmake(1.0, 0.0) : cmul(x0, scale);
+          x1 = cmul(x1, scale); x2 = cmul(x2, scale); x3 = cmul(x3, scale);
+          a[rl * QR_LDA + c] = csub(t0, cmul(x0, wc));
+          a[(rl + 8) * QR_LDA + c] = csub(t1, cmul(x1, wc));
+          a[(rl + 16) * QR_LDA + c] = csub(t2, cmul(x2, wc));
+          a[(rl + 24) * QR_LDA + c] = csub(t3, cmul(x3, wc));
+        }
+        for (; rl < nloc; rl += 8) {
+          cplx x0 = a[rl * QR_LDA + j];
+          x0 = (r_begin + rl == j) ? cmake(1.0, 0.0) : cmul(x0, scale);
+          a[rl * QR_LDA + c] = csub(a[rl * QR_LDA + c], cmul(x0, wc));
+        }
+      }
+      __syncwarp();
+      // column j itself: lane l of warp g rewrites row rl0 + 8*l (every row of the slab belongs to exactly one warp)
+      for (int rl = rl0 + 8 * c; rl < nloc; rl += 8 * 32) {
         const int r = r_begin + rl;
-        const cplx xj = a[rl * QR_LDA + j];
-        const cplx v = r == j ? cmake(1.0, 0.0) : cmul(xj, scale);
-        cplx t = a[rl * QR_LDA + c];
-        __syncwarp();
-        if (c > j) t = csub(t, cmul(v, wc));
-        else if (c == j) t = r == j ? cmake(beta, 0.0) : v;
-        a[rl * QR_LDA + c] = t;
+        a[rl * QR_LDA + j] = (r == j) ? cmake(beta, 0.0) : cmul(a[rl * QR_LDA + j], scale);
       }
     }
-    if (rank == 0) {
-      // T(0:j,j) = -tau * T(0:j,0:j) * g ; T(j,j) = tau   (zlarft, forward/columnwise); thread (i=c, k = g mod 8)
-      __syncthreads();
-      cplx acc = cmake(0.0, 0.0);
-      if (c < j)
-        for (int k = c + ((g - c) & 7); k < j; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
-      tpart[g][c] = acc;
-      __syncthreads();
-      if (g == 0) {
-        if (c < j) {
-          cplx t = tpart[0][c];
+    __syncthreads();
+  }
+  if (rank == 0) {   // T column of the last reflector
+    const int jp = nb - 1;
+    cplx acc = cmake(0.0, 0.0);
+    if (c < jp)
+      for (int k = c + ((g - c) & 7); k < jp; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
+    tpart[g][c] = acc;
+    __syncthreads();
+    if (g == 0) {
+      if (c < jp) {
+        cplx tt = tpart[0][c];
 #pragma unroll
-          for (int w = 1; w < 8; ++w) t = cadd(t, tpart[w][c]);
-          Tsm[c][j] = cneg(cmul(tau, t));
-        } else if (c == j) {
-          Tsm[j][j] = tau;
-        }
+        for (int w = 1; w < 8; ++w) tt = cadd(tt, tpart[w][c]);
+        Tsm[c][jp] = cneg(cmul(tau_s[jp], tt));
+      } else if (c == jp) {
+        Tsm[jp][jp] = tau_s[jp];
       }
     }
     __syncthreads();

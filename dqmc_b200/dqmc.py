@@ -289,6 +289,11 @@ class DQMC:
         self._chk(self.lib.dqmc_bench_kernel(self._ctx, which, reps, C.byref(ms)))
         return ms.value
 
+    def lu_profile(self, enable=True, read=False):
+        out = np.zeros(16, dtype=np.int64)
+        self._chk(self.lib.dqmc_lu_profile(self._ctx, int(enable), out.ctypes.data_as(_l._I64) if read else None))
+        return out
+
     def kernel_launches(self):
         return int(self.lib.dqmc_kernel_launches(self._ctx))
 
