@@ -61,23 +61,38 @@ __device__ __forceinline__ cplx det3(cplx a, cplx b, cplx c, cplx d, cplx e, cpl
   return cadd(csub(cmul(a, t1), cmul(b, t2)), cmul(c, t3));
 }
 
-// cosh(x) and sinh(x)/x-style pieces from one expm1 (x >= 0, small): accurate without cancellation
-__device__ __forceinline__ void cosh_sinh(double x, double* ch, double* sh) {
-  const double em1 = expm1(x);
-  const double q = em1 / (em1 + 1.0);
-  *sh = 0.5 * (em1 + q);
-  *ch = 1.0 + 0.5 * em1 * q;
+// cosh(x) and sinh(x)/x as functions of z = x^2 (Taylor series, |x| <= 1: truncation < 1e-18), so that neither a square
+// root nor a division by |phi| is needed; larger arguments fall back to expm1.
+__device__ __forceinline__ void cosh_sinhc(double z, double* ch, double* shc) {
+  if (z <= 1.0) {
+    double c = 1.0 / 2432902008176640000.0, s = 1.0 / 51090942171709440000.0;   // 1/20!, 1/21!
+    c = fma(c, z, 1.0 / 6402373705728000.0);  s = fma(s, z, 1.0 / 121645100408832000.0);   // 18!, 19!
+    c = fma(c, z, 1.0 / 20922789888000.0);    s = fma(s, z, 1.0 / 355687428096000.0);      // 16!, 17!
+    c = fma(c, z, 1.0 / 87178291200.0);       s = fma(s, z, 1.0 / 1307674368000.0);        // 14!, 15!
+    c = fma(c, z, 1.0 / 479001600.0);         s = fma(s, z, 1.0 / 6227020800.0);           // 12!, 13!
+    c = fma(c, z, 1.0 / 3628800.0);           s = fma(s, z, 1.0 / 39916800.0);             // 10!, 11!
+    c = fma(c, z, 1.0 / 40320.0);             s = fma(s, z, 1.0 / 362880.0);               // 8!, 9!
+    c = fma(c, z, 1.0 / 720.0);               s = fma(s, z, 1.0 / 5040.0);                 // 6!, 7!
+    c = fma(c, z, 1.0 / 24.0);                s = fma(s, z, 1.0 / 120.0);                  // 4!, 5!
+    c = fma(c, z, 0.5);                       s = fma(s, z, 1.0 / 6.0);                    // 2!, 3!
+    *ch = fma(c, z, 1.0);
+    *shc = fma(s, z, 1.0);
+  } else {
+    const double x = sqrt(z), em1 = expm1(x), q = em1 / (em1 + 1.0);
+    *ch = 1.0 + 0.5 * em1 * q;
+    *shc = 0.5 * (em1 + q) / x;
+  }
 }
 
-// One warp evaluates the proposal at `site` (proposal draws at unif[posp..posp+2], accept draw at posp+3).
-// prev_site / prev_new: a site whose field value must be read as prev_new instead of fs[] (or -1).
-__device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, int site, long long posp, int prev_site,
-                                        double pn1, double pn2, double pn3, int sl_earlier, int sl_later, Prep* out,
-                                        int* exhausted) {
+// One warp evaluates the proposal at `site`: proposal draws uw[off..off+2], accept draw uw[off+3] (uw = this slice's
+// window of the uniform stream in shared memory).  prev_site / pn*: a site whose field value must be read as pn*
+// instead of fs[] (or -1).  tn = phi(l+1) + phi(l-1) per site, nbr = spatial neighbour table, both in shared memory.
+__device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, const double* tn, const int* nbr, const double* uw,
+                                        int off, int navail, int site, int prev_site, double pn1, double pn2, double pn3,
+                                        Prep* out, int* exhausted) {
   const int lane = threadIdx.x & 31;
-  const int N = a.nsites;
   double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-  if (posp + 4 <= a.nunif) { u0 = a.unif[posp]; u1 = a.unif[posp + 1]; u2 = a.unif[posp + 2]; u3 = a.unif[posp + 3]; }
+  if (off + 4 <= navail) { u0 = uw[off]; u1 = uw[off + 1]; u2 = uw[off + 2]; u3 = uw[off + 3]; }
   else *exhausted = 1;
   const double o1 = fs[3 * site], o2 = fs[3 * site + 1], o3 = fs[3 * site + 2];
   // randuniform (dqmc_framework.jl:628): -b + 2*b*rand(); no FMA contraction so the field stays bit-identical
@@ -91,13 +106,11 @@ __device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, int s
   const double sq_diff = nsq - osq, pow4_diff = nsq * nsq - osq * osq;
   double dS;
   if (!a.edrun) {
-    const double* he = a.hs + 3 * ((size_t)site + (size_t)N * sl_earlier);
-    const double* hl = a.hs + 3 * ((size_t)site + (size_t)N * sl_later);
-    const double t1 = hl[0] + he[0], t2 = hl[1] + he[1], t3 = hl[2] + he[2];
+    const double t1 = tn[3 * site], t2 = tn[3 * site + 1], t3 = tn[3 * site + 2];
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) {
-      const int j = a.nbr[4 * site + nb];
+      const int j = nbr[4 * site + nb];
       const bool sub = (j == prev_site);
       s1 += sub ? pn1 : fs[3 * j];
       s2 += sub ? pn2 : fs[3 * j + 1];
@@ -110,24 +123,44 @@ __device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, int s
     dS = a.dtau * (0.5 * a.r * sq_diff);
   }
   const double e_dS = exp(-dS);
-  // interaction_matrix_exp_op!: old value with power -1, new value with power +1
-  const double on = sqrt(osq), nn = sqrt(nsq);
-  double C1, s1h, C2, s2h;
-  cosh_sinh(a.lam_dtau * on, &C1, &s1h);
-  cosh_sinh(a.lam_dtau * nn, &C2, &s2h);
-  const double sh1 = -s1h / on, sh2 = s2h / nn;
+  // interaction_matrix_exp_op!: old value with power -1, new value with power +1;  sinh(x)/|phi| = lam*dtau * sinh(x)/x
+  const double l2 = a.lam_dtau * a.lam_dtau;
+  double C1, q1, C2, q2;
+  cosh_sinhc(l2 * osq, &C1, &q1);
+  cosh_sinhc(l2 * nsq, &C2, &q2);
+  const double sh1 = -a.lam_dtau * q1, sh2 = a.lam_dtau * q2;
   const cplx S1 = cmake(-o1 * sh1, o2 * sh1), S2 = cmake(-n1 * sh2, n2 * sh2);
   const double R1 = -o3 * sh1, R2 = -n3 * sh2;
+  // E = C*1 + Y(S,R),  Y = [0 S 0 R; cS 0 -R 0; 0 -R 0 cS; R 0 S 0],  so  E1 E2 - 1 = (C1 C2 - 1) + C1 Y2 + C2 Y1 + Y1 Y2 with
+  // Y1 Y2 = diag(a, ca, ca, a) + b (e02 + e31) - cb (e13 + e20),  a = S1 cS2 + R1 R2,  b = R1 S2 - S1 R2.
   if (lane < 16) {
     const int r = lane >> 2, c = lane & 3;
-    cplx acc = cmake(r == c ? -1.0 : 0.0, 0.0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cfma(acc, evop_elem(r, k, C1, S1, R1), evop_elem(k, c, C2, S2, R2));
-    out->D[lane] = acc;
+    const cplx av = cmake(S1.x * S2.x + S1.y * S2.y + R1 * R2, S1.y * S2.x - S1.x * S2.y);
+    const cplx bv = cmake(R1 * S2.x - S1.x * R2, R1 * S2.y - S1.y * R2);
+    const cplx ys = cmake(C1 * S2.x + C2 * S1.x, C1 * S2.y + C2 * S1.y);     // S-type entry of C1 Y2 + C2 Y1
+    const double yr = C1 * R2 + C2 * R1;                                      // R-type entry
+    // kind per (r,c): 0 a, 1 conj a, 2 S, 3 conj S, 4 R, 5 -R, 6 b, 7 -conj b
+    const unsigned long long kinds = 0x264315775134620ull;   // nibble (r*4+c): see table below
+    // (0,0)0 (0,1)2 (0,2)6 (0,3)4 | (1,0)3 (1,1)1 (1,2)5 (1,3)7 | (2,0)7 (2,1)5 (2,2)1 (2,3)3 | (3,0)4 (3,1)6 (3,2)2 (3,3)0
+    const int kind = (int)((kinds >> (4 * lane)) & 7ull);
+    cplx v;
+    switch (kind) {
+      case 0: v = cmake(C1 * C2 - 1.0 + av.x, av.y); break;
+      case 1: v = cmake(C1 * C2 - 1.0 + av.x, -av.y); break;
+      case 2: v = ys; break;
+      case 3: v = cconj(ys); break;
+      case 4: v = cmake(yr, 0.0); break;
+      case 5: v = cmake(-yr, 0.0); break;
+      case 6: v = bv; break;
+      default: v = cmake(-bv.x, bv.y); break;
+    }
+    (void)r; (void)c;
+    out->D[lane] = v;
   }
   if (lane == 0) {
     out->nw[0] = n1; out->nw[1] = n2; out->nw[2] = n3;
-    out->e_dS = e_dS; out->mlog = -log(e_dS); out->u3 = u3;
+    // the reference accumulates -log(exp(-dS)) (local_updates.jl:34) = dS up to one rounding of exp/log
+    out->e_dS = e_dS; out->mlog = dS; out->u3 = u3;
   }
 }
 
@@ -144,8 +177,12 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   cplx* grow = sp; sp += (size_t)2 * rpc * 4;               // [2][rpc][4] G[site+kN, c] for my cols
   cplx* FA = sp; sp += 64 * 36;                             // flush staging: 64 rows x 32 k (+4 pad)
   cplx* FB = sp; sp += 64 * 36;
-  double* fs = reinterpret_cast<double*>(sp);               // [3*N] field of this slice
-  __shared__ cplx g4e[2][16], g4r[16], Mm[16], Cof[16], Minv[16], gcc[64 * 4], grc[64 * 4];
+  double* fs = reinterpret_cast<double*>(sp);               // [3N] field of this slice
+  double* tn = fs + 3 * N;                                  // [3N] phi(l+1) + phi(l-1)
+  double* uw = tn + 3 * N;                                  // [4N] this slice's window of the uniform stream
+  int* nbr = reinterpret_cast<int*>(uw + 4 * N);            // [4N] spatial neighbours
+  __shared__ cplx g4e[2][16], g4r[16], Gx1[16], Gx2[16], X1s[16], X2s[16], T1s[16], T2s[16];
+  __shared__ cplx Mm[16], Cof[16], Minv[16], gcc[64 * 4], grc[64 * 4];
   __shared__ Prep prep[2][3];
   __shared__ int s_accept, s_scn, s_exh;
 
@@ -154,23 +191,34 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   const int nown = max(0, min(n, row0 + rpc) - row0);
   const int sl = a.slice;
   const int sl_later = (sl + 1) % a.nslices, sl_earlier = (sl + a.nslices - 1) % a.nslices;
+  const long long pos0 = *a.pos;
+  const int navail = (int)max(0LL, min((long long)4 * N, a.nunif - pos0));
 
-  for (int e = tid; e < 3 * N; e += blockDim.x) fs[e] = a.hs[(size_t)3 * N * sl + e];
+  for (int e = tid; e < 3 * N; e += blockDim.x) {
+    fs[e] = a.hs[(size_t)3 * N * sl + e];
+    tn[e] = a.hs[(size_t)3 * N * sl_later + e] + a.hs[(size_t)3 * N * sl_earlier + e];
+  }
+  for (int e = tid; e < 4 * N; e += blockDim.x) {
+    nbr[e] = a.nbr[e];
+    uw[e] = e < navail ? a.unif[pos0 + e] : 0.0;
+  }
   if (tid == 0) s_exh = 0;
-  long long pos = *a.pos;
+  int off = 0;                                              // stream position relative to pos0
   long long nacc = 0;
   double dS_sum = 0.0;
-  int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0;
+  int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0, prev_acc = 0;
   // optional cycle profile of CTA 0: arrival stamps before the two CTA barriers of an iteration (a clock read right
   // after bar.sync would capture the barrier's issue, not its release)
   const bool prof = (a.prof != nullptr) && blockIdx.x == 0;
   __shared__ long long stampA[8], stampB[8];
-  long long p_role[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
+  __shared__ long long p_role[8];
+  if (tid < 8) p_role[tid] = 0;
+  long long p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
   __syncthreads();
   const long long t_begin = clock64();
   rel_prev = t_begin;
 
-  // G-derived data of `site` into buffer bb (all threads of the CTA or the 128 prefetch threads; tp = local index)
+  // G-derived data of `site` into buffer bb (tp = index among the nth participating threads)
   auto fetch_G = [&](int site, int bb, int tp, int nth) {
     if (tp < 16) g4r[tp] = ldcg2(a.G + (size_t)(site + (tp >> 2) * N) * n + site + (tp & 3) * N);   // [r + 4c]
     for (int e = tp; e < nown * 4; e += nth) {
@@ -182,7 +230,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 
   // ---- prologue: site 0
   fetch_G(0, 0, tid, 256);
-  if (warp == 1) do_prep(a, fs, 0, pos, -1, 0.0, 0.0, 0.0, sl_earlier, sl_later, &prep[0][0], &s_exh);
+  if (warp == 1) do_prep(a, fs, tn, nbr, uw, 0, navail, 0, -1, 0.0, 0.0, 0.0, &prep[0][0], &s_exh);
   __syncthreads();
   if (tid < 16) g4e[0][tid] = g4r[tid];
   __syncthreads();
@@ -197,16 +245,13 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       const Prep& P = prep[b][s_cur];
       const int r = (lane >> 2) & 3, c = lane & 3;
       if (lane < 16) {   // M = 1 + Delta * (1 - G_eff)
-        cplx t0, t1, t2, t3;
-        {
-          cplx g0 = g4e[b][0 + 4 * c], g1 = g4e[b][1 + 4 * c], g2 = g4e[b][2 + 4 * c], g3 = g4e[b][3 + 4 * c];
-          g0 = cmake((c == 0 ? 1.0 : 0.0) - g0.x, -g0.y);
-          g1 = cmake((c == 1 ? 1.0 : 0.0) - g1.x, -g1.y);
-          g2 = cmake((c == 2 ? 1.0 : 0.0) - g2.x, -g2.y);
-          g3 = cmake((c == 3 ? 1.0 : 0.0) - g3.x, -g3.y);
-          t0 = cmul(P.D[r * 4 + 0], g0); t1 = cmul(P.D[r * 4 + 1], g1);
-          t2 = cmul(P.D[r * 4 + 2], g2); t3 = cmul(P.D[r * 4 + 3], g3);
-        }
+        cplx g0 = g4e[b][0 + 4 * c], g1 = g4e[b][1 + 4 * c], g2 = g4e[b][2 + 4 * c], g3 = g4e[b][3 + 4 * c];
+        g0 = cmake((c == 0 ? 1.0 : 0.0) - g0.x, -g0.y);
+        g1 = cmake((c == 1 ? 1.0 : 0.0) - g1.x, -g1.y);
+        g2 = cmake((c == 2 ? 1.0 : 0.0) - g2.x, -g2.y);
+        g3 = cmake((c == 3 ? 1.0 : 0.0) - g3.x, -g3.y);
+        const cplx t0 = cmul(P.D[r * 4 + 0], g0), t1 = cmul(P.D[r * 4 + 1], g1);
+        const cplx t2 = cmul(P.D[r * 4 + 2], g2), t3 = cmul(P.D[r * 4 + 3], g3);
         cplx m = cadd(cadd(t0, t1), cadd(t2, t3));
         if (r == c) m.x += 1.0;
         Mm[r * 4 + c] = m;
@@ -228,7 +273,11 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       else { acc_flag = (P.u3 < p_acc) ? 1 : 0; scn = acc_flag ? 2 : 0; }
       if (lane == 0) { s_accept = acc_flag; s_scn = scn; }
       if (acc_flag) {
-        if (lane < 16) Minv[r * 4 + c] = cdiv(Cof[c * 4 + r], det);
+        if (lane < 16) {
+          const double id = 1.0 / (det.x * det.x + det.y * det.y);
+          const cplx dinv = cmake(det.x * id, -det.y * id);
+          Minv[r * 4 + c] = cmul(Cof[c * 4 + r], dinv);
+        }
         nacc++;
         dS_sum += P.mlog;
       }
@@ -237,35 +286,81 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       if (have_next) {
         const int sc = warp - 1;                                  // 0 rejected, 1 accepted (no draw), 2 accepted (draw)
         const Prep& Pc = prep[b][s_cur];
-        const long long posp = pos + (sc == 1 ? 3 : 4);
-        do_prep(a, fs, i + 1, posp, sc == 0 ? -1 : i, Pc.nw[0], Pc.nw[1], Pc.nw[2], sl_earlier, sl_later, &prep[nb][sc], &s_exh);
+        do_prep(a, fs, tn, nbr, uw, off + (sc == 1 ? 3 : 4), navail, i + 1, sc == 0 ? -1 : i, Pc.nw[0], Pc.nw[1], Pc.nw[2],
+                &prep[nb][sc], &s_exh);
       }
     } else {
+      const int tp = tid - 128;
+      // ---- loads: everything is issued before anything is waited for
+      // (G) plain L2 loads: 4x4 block of site i+1, the two cross blocks between sites i+1 and i, my rows/cols of G
       if (have_next) {
-        const int tp = tid - 128, site = i + 1;
-        for (int e = tp; e < 8 * np; e += 128) {
-          const int w = e / (4 * np), rem = e - w * 4 * np, k = rem / np, p = rem - k * np;
-          const cplx* X = w ? Bmb : Atb;
-          cplx* Xs = (w ? Bs4 : As4) + (nb * 4 + k) * ldk;
-          Xs[p] = ld_valid(X + (size_t)(site + k * N) * ldk + p);
+        const int site = i + 1;
+        if (tp < 16) g4r[tp] = ldcg2(a.G + (size_t)(site + (tp >> 2) * N) * n + site + (tp & 3) * N);            // [r + 4c]
+        else if (tp < 32) { const int q = tp - 16; Gx1[q] = ldcg2(a.G + (size_t)(i + (q & 3) * N) * n + site + (q >> 2) * N); }   // [r*4+k] = G[i+1+rN, i+kN]
+        else if (tp < 48) { const int q = tp - 32; Gx2[q] = ldcg2(a.G + (size_t)(site + (q & 3) * N) * n + i + (q >> 2) * N); }   // [k*4+c] = G[i+kN, i+1+cN]
+        for (int e = tp; e < nown * 4; e += 128) {
+          const int rl = e >> 2, k = e & 3;
+          gcol[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(site + k * N) * n + row0 + rl);
+          grow[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(row0 + rl) * n + site + k * N);
         }
-        fetch_G(site, nb, tp, 128);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int o = tp >> 3, q = tp & 7, r = o & 3, c = o >> 2;   // 16 outputs x 8 partial lanes
-        cplx acc = cmake(0.0, 0.0);
-        for (int p = q; p < np; p += 8) cfma(acc, As4[(nb * 4 + r) * ldk + p], Bs4[(nb * 4 + c) * ldk + p]);
+      }
+      // (A/B) entries of the pending factors, published by their owner CTAs (spin on the NaN sentinel):
+      //   slot 0: the 4 newest columns for the rows/cols of site i (if site i-1 was accepted)
+      //   slots 1..: all np pending columns for the rows/cols of site i+1
+      // thread tp owns one (factor w, row/col k) pair and the pending columns p = tp/8 + 16u
+      {
+        const int w8 = (tp >> 2) & 1, k8 = tp & 3, p8 = tp >> 3;
+        const cplx* sbase = (w8 ? Bmb : Atb) + (size_t)(i + 1 + k8 * N) * ldk;
+        cplx* dbase = (w8 ? Bs4 : As4) + (nb * 4 + k8) * ldk;
+        const int w0 = (tp >> 4) & 1, k0 = (tp & 15) >> 2, kp = tp & 3;
+        const bool ok0 = prev_acc && tp < 32;
+        const cplx* s0 = (w0 ? Bmb : Atb) + (size_t)(i + k0 * N) * ldk + (ok0 ? np - 4 + kp : 0);
+        cplx* d0 = (w0 ? Bs4 : As4) + (b * 4 + k0) * ldk + (ok0 ? np - 4 + kp : 0);
+        unsigned long long vx[9], vy[9];
+        if (ok0) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[8]), "=l"(vy[8]) : "l"(s0) : "memory");
 #pragma unroll
-        for (int s = 4; s > 0; s >>= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+        for (int u = 0; u < 8; ++u)
+          if (have_next && p8 + 16 * u < np)
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
+        if (ok0) {
+          while (vx[8] == LU_SENT || vy[8] == LU_SENT)
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[8]), "=l"(vy[8]) : "l"(s0) : "memory");
+          *d0 = make_double2(__longlong_as_double((long long)vx[8]), __longlong_as_double((long long)vy[8]));
         }
-        if (q == 0) g4e[nb][o] = cadd(g4r[o], acc);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (have_next && p8 + 16 * u < np) {
+            while (vx[u] == LU_SENT || vy[u] == LU_SENT)
+              asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
+            dbase[p8 + 16 * u] = make_double2(__longlong_as_double((long long)vx[u]), __longlong_as_double((long long)vy[u]));
+          }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- partial sums over the pending columns: G_eff block of site i+1 and the two cross blocks (48 outputs x 2 threads)
+      if (have_next && tp < 96) {
+        const int o = tp >> 1, h = tp & 1, which = o >> 4, idx = o & 15;
+        const cplx *pa, *pb;
+        cplx base;
+        if (which == 0) { pa = As4 + (nb * 4 + (idx & 3)) * ldk; pb = Bs4 + (nb * 4 + (idx >> 2)) * ldk; base = g4r[idx]; }
+        else if (which == 1) { pa = As4 + (nb * 4 + (idx >> 2)) * ldk; pb = Bs4 + (b * 4 + (idx & 3)) * ldk; base = Gx1[idx]; }
+        else { pa = As4 + (b * 4 + (idx >> 2)) * ldk; pb = Bs4 + (nb * 4 + (idx & 3)) * ldk; base = Gx2[idx]; }
+        cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
+        int p = h;
+        for (; p + 2 < np; p += 4) { cfma(acc0, pa[p], pb[p]); cfma(acc1, pa[p + 2], pb[p + 2]); }
+        for (; p < np; p += 2) cfma(acc0, pa[p], pb[p]);
+        cplx acc = cadd(acc0, acc1);
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+        if (h == 0) {
+          acc = cadd(acc, base);
+          if (which == 0) g4e[nb][idx] = acc; else if (which == 1) X1s[idx] = acc; else X2s[idx] = acc;
+        }
       }
     }
     if (prof && lane == 0) stampA[warp] = clock64();
     __syncthreads();
     const int accepted = s_accept, scn = s_scn;
-    pos += (scn == 1) ? 3 : 4;
+    off += (scn == 1) ? 3 : 4;
     // ================= stage 2: accepted -> append my slice of the new columns of A / rows of B =================
     if (accepted) {
       const Prep& P = prep[b][s_cur];
@@ -273,73 +368,87 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         fs[3 * i + tid] = P.nw[tid];
         if (blockIdx.x == 0) a.hs[(size_t)3 * N * sl + 3 * i + tid] = P.nw[tid];
       }
-      {   // G_eff[r, i+kN] for my rows and G_eff[i+kN, c] for my columns: 4 threads per dot product over the pending columns
-        const int task = tid >> 2, q = tid & 3;
+      if (warp == 0) {
+        // G_eff block of site i+1 gets the new rank-4 term without waiting for anybody:
+        //   += (G_eff[i+1+rN, i+kN] M^-1) (Delta G_eff[i+kN, i+1+cN])
+        if (have_next) {
+          const int r = (lane >> 2) & 3, c = lane & 3;
+          cplx acc = cmake(0.0, 0.0);
+          if (lane < 16) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) cfma(acc, X1s[r * 4 + kk], Minv[kk * 4 + c]);
+            T1s[r * 4 + c] = acc;
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[r * 4 + kk], X2s[kk * 4 + c]);
+            T2s[r * 4 + c] = acc;
+          }
+          __syncwarp();
+          if (lane < 16) {
+            const int rr = lane & 3, cc = lane >> 2;       // g4e layout [r + 4c]
+            cplx g = g4e[nb][lane];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) cfma(g, T1s[rr * 4 + kk], T2s[kk * 4 + cc]);
+            g4e[nb][lane] = g;
+          }
+        }
+      } else {
+        // warps 1-7: G_eff[r, i+kN] for my rows and G_eff[i+kN, c] for my columns (2 threads per dot product), then my
+        // slice of the new columns:  A_new[r,:] = (G_eff[r, i+kN] - delta) M^-1,  B_new[:,c] = Delta G_eff[i+kN, c]
+        const int t2 = tid - 32;
         const int half = nown * 4;
-        for (int t0 = 0; t0 < 2 * half; t0 += 64) {
-          const int t = t0 + task;
+        for (int t0 = 0; t0 < 2 * half; t0 += 112) {
+          const int t = t0 + (t2 >> 1), h = t2 & 1;
           const bool act = t < 2 * half;
           const bool isB = t >= half;
           const int tt = isB ? t - half : t;
-          const int rl = tt >> 2, k = tt & 3;
-          cplx acc = cmake(0.0, 0.0);
+          const int rl = tt >> 2, kq = tt & 3;
+          cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
           if (act) {
             const cplx* own = (isB ? Bown : Aown) + (size_t)rl * ldk;
-            const cplx* site = (isB ? As4 : Bs4) + (b * 4 + k) * ldk;
-            for (int p = q; p < np; p += 4) cfma(acc, own[p], site[p]);
+            const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * ldk;
+            int p = h;
+            for (; p + 2 < np; p += 4) { cfma(acc0, own[p], site[p]); cfma(acc1, own[p + 2], site[p + 2]); }
+            for (; p < np; p += 2) cfma(acc0, own[p], site[p]);
           }
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
-          if (act && q == 0) {
+          cplx acc = cadd(acc0, acc1);
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+          if (act && h == 0) {
             if (!isB) {
               cplx v = cadd(gcol[b * rpc * 4 + tt], acc);
-              if (row0 + rl == i + k * N) v.x -= 1.0;
+              if (row0 + rl == i + kq * N) v.x -= 1.0;
               gcc[tt] = v;
             } else {
               grc[tt] = cadd(grow[b * rpc * 4 + tt], acc);
             }
           }
         }
-      }
-      __syncthreads();
-      cplx* Atw = a.At + batch * bufstride;
-      cplx* Bmw = a.Bm + batch * bufstride;
-      for (int e = tid; e < nown * 8; e += blockDim.x) {
-        const bool isB = e >= nown * 4;
-        const int tt = isB ? e - nown * 4 : e;
-        const int rl = tt >> 2, k = tt & 3;
-        cplx acc = cmake(0.0, 0.0);
-        if (!isB) {   // A_new[r,:] = (G_eff[r, i+kN] - delta) M^-1
+        asm volatile("bar.sync 2, 224;" ::: "memory");
+        cplx* Atw = a.At + batch * bufstride;
+        cplx* Bmw = a.Bm + batch * bufstride;
+        for (int e = t2; e < nown * 8; e += 224) {
+          const bool isB = e >= nown * 4;
+          const int tt = isB ? e - nown * 4 : e;
+          const int rl = tt >> 2, kq = tt & 3;
+          cplx acc = cmake(0.0, 0.0);
+          if (!isB) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) cfma(acc, gcc[rl * 4 + kk], Minv[kk * 4 + k]);
-          Aown[(size_t)rl * ldk + np + k] = acc;
-          st_pub(Atw + (size_t)(row0 + rl) * ldk + np + k, acc);
-        } else {      // B_new[:,c] = Delta G_eff[i+kN, c]
+            for (int kk = 0; kk < 4; ++kk) cfma(acc, gcc[rl * 4 + kk], Minv[kk * 4 + kq]);
+            Aown[(size_t)rl * ldk + np + kq] = acc;
+            st_pub(Atw + (size_t)(row0 + rl) * ldk + np + kq, acc);
+          } else {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[k * 4 + kk], grc[rl * 4 + kk]);
-          Bown[(size_t)rl * ldk + np + k] = acc;
-          st_pub(Bmw + (size_t)(row0 + rl) * ldk + np + k, acc);
-        }
-      }
-      if (have_next) {   // the 4 new columns for the rows/columns of site i+1 (spin until their owners have published them)
-        if (tid < 32) {
-          const int w = tid >> 4, sub = tid & 15, k = sub >> 2, kp = sub & 3;
-          const cplx* X = w ? Bmw : Atw;
-          cplx* Xs = (w ? Bs4 : As4) + (nb * 4 + k) * ldk;
-          Xs[np + kp] = ld_valid(X + (size_t)(i + 1 + k * N) * ldk + np + kp);
-        }
-        __syncthreads();
-        if (tid < 16) {
-          const int r = tid & 3, c = tid >> 2;
-          cplx acc = g4e[nb][tid];
-#pragma unroll
-          for (int kp = 0; kp < 4; ++kp) cfma(acc, As4[(nb * 4 + r) * ldk + np + kp], Bs4[(nb * 4 + c) * ldk + np + kp]);
-          g4e[nb][tid] = acc;
+            for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[kq * 4 + kk], grc[rl * 4 + kk]);
+            Bown[(size_t)rl * ldk + np + kq] = acc;
+            st_pub(Bmw + (size_t)(row0 + rl) * ldk + np + kq, acc);
+          }
         }
       }
       kc++;
       np += 4;
     }
+    prev_acc = accepted;
     // ================= flush: G += A B over the pending 4*kc columns =================
     const bool do_flush = (kc == a.kmax || (i == N - 1 && kc > 0));
     if (do_flush) {
@@ -356,15 +465,27 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         for (int x = 0; x < 4; ++x)
 #pragma unroll
           for (int y = 0; y < 2; ++y) cr[x][y][0] = cr[x][y][1] = ci[x][y][0] = ci[x][y][1] = 0.0;
+        cplx ra[8], rb[8];
+        auto stage_load = [&](int k0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = tid + 256 * u, rr = e >> 5, kk = e & 31;
+            const bool kok = (k0 + kk) < K;
+            ra[u] = (kok && tm0 + rr < n) ? ldcg2(Atb + (size_t)(tm0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
+            rb[u] = (kok && tn0 + rr < n) ? ldcg2(Bmb + (size_t)(tn0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
+          }
+        };
+        stage_load(0);
         for (int k0 = 0; k0 < K; k0 += 32) {
           __syncthreads();
-          for (int e = tid; e < 64 * 32; e += blockDim.x) {
-            const int rr = e >> 5, kk = e & 31;
-            const bool kok = (k0 + kk) < K;
-            FA[rr * 36 + kk] = (kok && tm0 + rr < n) ? ldcg2(Atb + (size_t)(tm0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
-            FB[rr * 36 + kk] = (kok && tn0 + rr < n) ? ldcg2(Bmb + (size_t)(tn0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = tid + 256 * u, rr = e >> 5, kk = e & 31;
+            FA[rr * 36 + kk] = ra[u];
+            FB[rr * 36 + kk] = rb[u];
           }
           __syncthreads();
+          if (k0 + 32 < K) stage_load(k0 + 32);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             cplx av[4], bv[2];
@@ -383,6 +504,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
               }
           }
         }
+        cplx gv[4][2][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -390,12 +512,17 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
-              if (row < n && col < n) {
-                cplx* p = a.G + (size_t)col * n + row;
-                cplx v = ldcg2(p);
-                v.x += cr[x][y][e]; v.y += ci[x][y][e];
-                *p = v;
-              }
+              gv[x][y][e] = (row < n && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
+            }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
+              if (row < n && col < n)
+                a.G[(size_t)col * n + row] = cmake(gv[x][y][e].x + cr[x][y][e], gv[x][y][e].y + ci[x][y][e]);
             }
       }
       grid_barrier(a.bar, gridDim.x);
@@ -411,6 +538,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       batch ^= 1;
       kc = 0;
       np = 0;
+      prev_acc = 0;
       if (have_next) {   // G changed: refresh what was prefetched for site i+1
         fetch_G(i + 1, nb, tid, 256);
         __syncthreads();
@@ -437,7 +565,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   }
 
   if (blockIdx.x == 0 && tid == 0) {
-    *a.pos = pos;
+    *a.pos = pos0 + off;
     *a.accepted += nacc;
     *a.dS += dS_sum;
     if (s_exh) a.flags[0] = 1;
@@ -457,7 +585,8 @@ int local_updates_grid(int n, int num_sms, int* rpc) {
 
 size_t local_updates_smem(const LUArgs& a) {
   const int ldk = 4 * a.kmax;
-  return sizeof(cplx) * ((size_t)2 * a.rpc * ldk + 16 * ldk + 16 * a.rpc + 2 * 64 * 36) + sizeof(double) * 3 * a.nsites;
+  return sizeof(cplx) * ((size_t)2 * a.rpc * ldk + 16 * ldk + 16 * a.rpc + 2 * 64 * 36) + sizeof(double) * 10 * a.nsites +
+         sizeof(int) * 4 * a.nsites;
 }
 
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid) {
