@@ -171,7 +171,8 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        parallel.init_process_group("nccl")
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        parallel.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L, M, sm = cfg["L"], cfg["slices"], cfg["safe_mult"]
     N = L * L
     p = Params(L=L, slices=M, safe_mult=sm, delta_tau=MODEL["delta_tau"], lambda_=MODEL["lam"], r=MODEL["r"], c=MODEL["c"],

@@ -187,7 +187,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   c->unif = nullptr; c->unif_cap = c->unif_n = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
-  TRY(c, dmalloc(c, &c->d_prof, 16)); c->lu_prof = false;
+  TRY(c, dmalloc(c, &c->d_prof, 32)); c->lu_prof = false;
   TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
@@ -796,6 +796,17 @@ extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {
 
 extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t enable) {
   c->timing = enable != 0;
+  return 0;
+}
+
+// debug hook: per-phase cycle counters of the QR panel kernel (rank 0, thread 0), accumulated while enabled
+extern long long* g_qr_prof;
+extern "C" int dqmc_qr_profile(dqmc_ctx* c, int32_t enable, int64_t* out8) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaStreamSynchronize(c->st));
+  if (out8) CU(c, cudaMemcpy(out8, c->d_prof + 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemset(c->d_prof + 8, 0, sizeof(long long) * 8));
+  g_qr_prof = enable ? c->d_prof + 8 : nullptr;
   return 0;
 }
 

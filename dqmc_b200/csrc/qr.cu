@@ -14,8 +14,10 @@ namespace cg = cooperative_groups;
 #define QR_LDA 33
 __global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(256)
 qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
-                double* __restrict__ dabs_out, cplx* __restrict__ Tout) {
+                double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
   cg::cluster_group cl = cg::this_cluster();
+  long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define PSTAMP(k) do { if (prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
   const int rank = (int)cl.block_rank();
   const int rs = (m + QR_CL - 1) / QR_CL;
   const int r_begin = rank * rs;
@@ -60,6 +62,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       for (; rl < nloc; rl += 8) cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
       part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
     }
+    PSTAMP(0);
     if (rank == 0 && j > 0) {
       // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise), computed
       // in the shadow of this column's dot products; thread (i = c, k = g mod 8)
@@ -94,9 +97,12 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
         }
       }
     }
+    PSTAMP(1);
     cl.sync();
     // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
     cplx tc = xch[par][0][c], tj = xch[par][0][j];
+    if (prof) { if (tc.x == 1.2345e300) pc[5]++; }
+    PSTAMP(2);
 #pragma unroll
     for (int src = 1; src < QR_CL; ++src) { tc = cadd(tc, xch[par][src][c]); tj = cadd(tj, xch[par][src][j]); }
     const cplx alpha = rowv[par][j], rowc = rowv[par][c];
@@ -123,6 +129,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       gsm[c] = c < j ? gg : cmake(0.0, 0.0);
       if (c == 0) { tau_s[j] = tau; beta_s[j] = beta; }
     }
+    PSTAMP(3);
     // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j); column j <- v (below the diagonal) and beta (diagonal)
     {
       int rl0 = g;
@@ -153,8 +160,10 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
         a[rl * QR_LDA + j] = (r == j) ? cmake(beta, 0.0) : cmul(a[rl * QR_LDA + j], scale);
       }
     }
+    PSTAMP(4);
     __syncthreads();
   }
+  if (prof && rank == 0 && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
   if (rank == 0) {   // T column of the last reflector
     const int jp = nb - 1;
     cplx acc = cmake(0.0, 0.0);
@@ -314,13 +323,14 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
   }
 }
 
+long long* g_qr_prof = nullptr;
 static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
   const int rs = (m + QR_CL - 1) / QR_CL;
   const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * rs + 8);
   static size_t smem_lim = 0;
   if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
-  qr_panel_kernel<<<QR_CL, 256, smem, st>>>(A, lda, m, nb, tau, dabs, T);
+  qr_panel_kernel<<<QR_CL, 256, smem, st>>>(A, lda, m, nb, tau, dabs, T, g_qr_prof);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;

@@ -65,6 +65,7 @@ SIGNATURES = {
     "dqmc_test_zgemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, C.c_int, _D, C.c_int, _D, _D,
                                   C.c_int]),
     "dqmc_lu_profile": (C.c_int, [_P, C.c_int32, _I64]),
+    "dqmc_qr_profile": (C.c_int, [_P, C.c_int32, _I64]),
     "dqmc_kernel_launches": (C.c_int64, [_P]),
 }
 

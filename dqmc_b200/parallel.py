@@ -10,14 +10,17 @@ import torch
 import torch.distributed as dist
 
 
-def init_process_group(backend=None):
+def init_process_group(backend=None, device_id=None):
     """Rendezvous from the torchrun environment (RANK / WORLD_SIZE / MASTER_*); no-op for a single process."""
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1 or dist.is_initialized():
         return int(os.environ.get("RANK", "0")), world
     backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-    dist.init_process_group(backend=backend)
+    if device_id is not None:
+        dist.init_process_group(backend=backend, device_id=device_id)
+    else:
+        dist.init_process_group(backend=backend)
     return dist.get_rank(), dist.get_world_size()
 
 

@@ -120,6 +120,8 @@ int dqmc_test_zgemm(dqmc_ctx* ctx, int opA, int opB, int M, int N, int K, const 
 /* cycle counters of the last local_updates launch: [0] total, [1] stage 1, [2] stage 2, [3] flush, [4] #flushes,
  * [5] accepts, [8..15] per-warp role time (debug) */
 int dqmc_lu_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out16);
+/* per-phase cycle counters of the QR panel kernel accumulated since the last call (debug) */
+int dqmc_qr_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out8);
 int64_t dqmc_kernel_launches(dqmc_ctx* ctx);   /* kernels launched by this context so far */
 
 #ifdef __cplusplus
