@@ -36,6 +36,8 @@ struct dqmc_ctx {
   int n, N, M, sm, nel, kmax;
   int num_sms;
   cudaStream_t st;
+  QrAsync qra;
+  bool lookahead;
   char err[512];
   // state (1-based like the reference)
   int current_slice, direction;
@@ -160,6 +162,10 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   CU(c, cudaGetDeviceProperties(&prop, p->device));
   c->num_sms = prop.multiProcessorCount;
   CU(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CU(c, cudaStreamCreateWithFlags(&c->qra.st2, cudaStreamNonBlocking));
+  CU(c, cudaEventCreateWithFlags(&c->qra.eA, cudaEventDisableTiming));
+  CU(c, cudaEventCreateWithFlags(&c->qra.eB, cudaEventDisableTiming));
+  c->lookahead = getenv("DQMC_NO_LOOKAHEAD") == nullptr;
   const size_t n = c->n, nn = n * n;
   TRY(c, dmalloc(c, &c->G, nn));
   TRY(c, dmalloc(c, &c->Gtmp, nn));
@@ -209,6 +215,9 @@ extern "C" int dqmc_destroy(dqmc_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < F_COUNT; ++i) { if (c->fop[i].idx) cudaFree(c->fop[i].idx); if (c->fop[i].val) cudaFree(c->fop[i].val); }
   cudaStreamDestroy(c->st);
+  cudaStreamDestroy(c->qra.st2);
+  cudaEventDestroy(c->qra.eA);
+  cudaEventDestroy(c->qra.eB);
   delete c;
   return 0;
 }
@@ -475,7 +484,7 @@ static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
   const int n = c->n;
   TRY(c, argsort_desc(c->st, c->colnorm, n, c->perm));
   TRY(c, gather_cols(c->st, c->W[0], n, n, c->perm, c->W[1], n, c->num_sms));
-  TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, nullptr, 0, 0, c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, nullptr, 0, 0, c->num_sms, c->lookahead ? &c->qra : nullptr));
   TRY(c, qr_form_q(c->st, c->W[1], n, n, c->tfac, Uout, n, c->num_sms));
   TRY(c, build_T(c->st, c->W[1], n, n, Dout, c->perm, c->W[2], n, c->num_sms));
   return 0;
@@ -517,7 +526,7 @@ static int calculate_greens_dev(dqmc_ctx* c) {
   TRY(c, zgemm(c->st, OP_C, OP_N, n, n, n, ONE, c->Ul, n, c->Ur, n, ZERO, c->W[0], n, c->num_sms));
   TRY(c, zgemm(c->st, OP_N, OP_C, n, n, n, ONE, c->Tl, n, c->Tr, n, ZERO, c->W[1], n, c->num_sms));
   TRY(c, loh_assemble(c->st, n, c->W[0], c->W[1], c->Dl, c->Dr, c->Ul, c->W[2], c->W[3], c->drp_inv, c->num_sms));
-  TRY(c, qr_factor(c->st, c->W[2], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[2], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms, c->lookahead ? &c->qra : nullptr));
   TRY(c, trsm_upper(c->st, c->W[2], n, n, c->W[3], n, n, c->trsm_work, c->drp_inv, c->num_sms));
   TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
   return 0;

@@ -345,17 +345,34 @@ static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cp
   return 0;
 }
 
+// Right-looking blocked QR with one-panel lookahead: while the cluster kernel factors panel k+1 on `st`, the block
+// reflector of panel k is applied to the rest of the trailing matrix (and to the right-hand side) on `st2`.
 int qr_factor(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac, cplx* rhs, int ldr,
-              int nrhs, int num_sms) {
+              int nrhs, int num_sms, const QrAsync* as) {
   (void)num_sms;
+  const bool la = as != nullptr && n > 2 * QR_NB;
   for (int j0 = 0, k = 0; j0 < n; j0 += QR_NB, ++k) {
     const int nb = min(QR_NB, n - j0), m = n - j0;
     cplx* P = A + (size_t)j0 * lda + j0;
     cplx* T = tfac + (size_t)k * QR_NB * QR_NB;
     if (launch_panel(st, P, lda, m, nb, tau + j0, dabs + j0, T)) return -1;
-    if (launch_larfb(st, P, lda, m, T, 1, P + (size_t)nb * lda, lda, n - j0 - nb)) return -1;
-    if (rhs && launch_larfb(st, P, lda, m, T, 1, rhs + j0, ldr, nrhs)) return -1;
+    const int ntrail = n - j0 - nb;
+    if (!la) {
+      if (launch_larfb(st, P, lda, m, T, 1, P + (size_t)nb * lda, lda, ntrail)) return -1;
+      if (rhs && launch_larfb(st, P, lda, m, T, 1, rhs + j0, ldr, nrhs)) return -1;
+      continue;
+    }
+    // columns of the next panel first (they must have received every earlier update: wait for st2's previous step)
+    const int nnext = min(QR_NB, ntrail);
+    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
+    if (launch_larfb(st, P, lda, m, T, 1, P + (size_t)nb * lda, lda, nnext)) return -1;
+    CUDA_TRY(cudaEventRecord(as->eA, st));
+    CUDA_TRY(cudaStreamWaitEvent(as->st2, as->eA, 0));
+    if (launch_larfb(as->st2, P, lda, m, T, 1, P + (size_t)(nb + nnext) * lda, lda, ntrail - nnext)) return -1;
+    if (rhs && launch_larfb(as->st2, P, lda, m, T, 1, rhs + j0, ldr, nrhs)) return -1;
+    CUDA_TRY(cudaEventRecord(as->eB, as->st2));
   }
+  if (la) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
   return 0;
 }
 

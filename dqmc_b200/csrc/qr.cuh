@@ -9,11 +9,16 @@
 #define QR_NB 32      // panel width
 #define QR_CL 8       // CTAs per thread-block cluster in the panel factorization
 
+struct QrAsync {      // second stream + two events for the panel lookahead (nullptr = everything on one stream)
+  cudaStream_t st2;
+  cudaEvent_t eA, eB;
+};
+
 // Householder QR of the n x n matrix A (in place: R in the upper triangle, V below, tau, |R_ii| in dabs).
 // tfac receives ceil(n/32) compact-WY T factors (32x32, column-major, ld 32).  If rhs != nullptr,
 // Q^H is applied to the n x nrhs matrix rhs as the factorization proceeds.
 int qr_factor(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac,
-              cplx* rhs, int ldr, int nrhs, int num_sms);
+              cplx* rhs, int ldr, int nrhs, int num_sms, const QrAsync* as);
 // Q (n x n, explicit) from the output of qr_factor.
 int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, cplx* Q, int ldq, int num_sms);
 // X = R^{-1} Y in place in Y (n x nrhs); R = upper triangle of A.  work: ceil(n/32)*1024 cplx.
