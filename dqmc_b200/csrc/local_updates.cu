@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   int off = 0;                                              // stream position relative to pos0
   long long nacc = 0;
   double dS_sum = 0.0;
-  int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0, prev_acc = 0;
+  int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0;
   // optional cycle profile of CTA 0: arrival stamps before the two CTA barriers of an iteration (a clock read right
   // after bar.sync would capture the barrier's issue, not its release)
   const bool prof = (a.prof != nullptr) && blockIdx.x == 0;
@@ -304,29 +304,18 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           grow[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(row0 + rl) * n + site + k * N);
         }
       }
-      // (A/B) entries of the pending factors, published by their owner CTAs (spin on the NaN sentinel):
-      //   slot 0: the 4 newest columns for the rows/cols of site i (if site i-1 was accepted)
-      //   slots 1..: all np pending columns for the rows/cols of site i+1
+      // (A/B) all np pending columns for the rows/cols of site i+1, published by their owner CTAs (spin on the NaN
+      // sentinel).  The current site's newest columns never come from memory: stage 2 derives them locally.
       // thread tp owns one (factor w, row/col k) pair and the pending columns p = tp/8 + 16u
       {
         const int w8 = (tp >> 2) & 1, k8 = tp & 3, p8 = tp >> 3;
         const cplx* sbase = (w8 ? Bmb : Atb) + (size_t)(i + 1 + k8 * N) * ldk;
         cplx* dbase = (w8 ? Bs4 : As4) + (nb * 4 + k8) * ldk;
-        const int w0 = (tp >> 4) & 1, k0 = (tp & 15) >> 2, kp = tp & 3;
-        const bool ok0 = prev_acc && tp < 32;
-        const cplx* s0 = (w0 ? Bmb : Atb) + (size_t)(i + k0 * N) * ldk + (ok0 ? np - 4 + kp : 0);
-        cplx* d0 = (w0 ? Bs4 : As4) + (b * 4 + k0) * ldk + (ok0 ? np - 4 + kp : 0);
-        unsigned long long vx[9], vy[9];
-        if (ok0) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[8]), "=l"(vy[8]) : "l"(s0) : "memory");
+        unsigned long long vx[8], vy[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (have_next && p8 + 16 * u < np)
             asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
-        if (ok0) {
-          while (vx[8] == LU_SENT || vy[8] == LU_SENT)
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[8]), "=l"(vy[8]) : "l"(s0) : "memory");
-          *d0 = make_double2(__longlong_as_double((long long)vx[8]), __longlong_as_double((long long)vy[8]));
-        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (have_next && p8 + 16 * u < np) {
@@ -357,6 +346,38 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         }
       }
     }
+    if (warp < 4) {
+      // speculative part of a possible accept (does not depend on the decision): G_eff[r, i+kN] - delta for my rows and
+      // G_eff[i+kN, c] for my columns, 2 threads per dot product over the pending columns
+      const int half = nown * 4;
+      for (int t0 = 0; t0 < 2 * half; t0 += 64) {
+        const int t = t0 + (tid >> 1), h = tid & 1;
+        const bool act = t < 2 * half;
+        const bool isB = t >= half;
+        const int tt = isB ? t - half : t;
+        const int rl = tt >> 2, kq = tt & 3;
+        cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
+        if (act) {
+          const cplx* own = (isB ? Bown : Aown) + (size_t)rl * ldk;
+          const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * ldk;
+          int p = h;
+          for (; p + 2 < np; p += 4) { cfma(acc0, own[p], site[p]); cfma(acc1, own[p + 2], site[p + 2]); }
+          for (; p < np; p += 2) cfma(acc0, own[p], site[p]);
+        }
+        cplx acc = cadd(acc0, acc1);
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+        if (act && h == 0) {
+          if (!isB) {
+            cplx v = cadd(gcol[b * rpc * 4 + tt], acc);
+            if (row0 + rl == i + kq * N) v.x -= 1.0;
+            gcc[tt] = v;
+          } else {
+            grc[tt] = cadd(grow[b * rpc * 4 + tt], acc);
+          }
+        }
+      }
+    }
     if (prof && lane == 0) stampA[warp] = clock64();
     __syncthreads();
     const int accepted = s_accept, scn = s_scn;
@@ -383,6 +404,10 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
             for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[r * 4 + kk], X2s[kk * 4 + c]);
             T2s[r * 4 + c] = acc;
           }
+          // T1 = rows i+1+rN of the new A columns, T2 = columns i+1+cN of the new B rows: the next site's copies are
+          // complete without a round trip through memory
+          if (lane < 16) As4[(nb * 4 + r) * ldk + np + c] = acc;
+          else Bs4[(nb * 4 + c) * ldk + np + r] = acc;
           __syncwarp();
           if (lane < 16) {
             const int rr = lane & 3, cc = lane >> 2;       // g4e layout [r + 4c]
@@ -393,38 +418,8 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           }
         }
       } else {
-        // warps 1-7: G_eff[r, i+kN] for my rows and G_eff[i+kN, c] for my columns (2 threads per dot product), then my
-        // slice of the new columns:  A_new[r,:] = (G_eff[r, i+kN] - delta) M^-1,  B_new[:,c] = Delta G_eff[i+kN, c]
+        // warps 1-7: my slice of the new columns:  A_new[r,:] = (G_eff[r, i+kN] - delta) M^-1,  B_new[:,c] = Delta G_eff[i+kN, c]
         const int t2 = tid - 32;
-        const int half = nown * 4;
-        for (int t0 = 0; t0 < 2 * half; t0 += 112) {
-          const int t = t0 + (t2 >> 1), h = t2 & 1;
-          const bool act = t < 2 * half;
-          const bool isB = t >= half;
-          const int tt = isB ? t - half : t;
-          const int rl = tt >> 2, kq = tt & 3;
-          cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
-          if (act) {
-            const cplx* own = (isB ? Bown : Aown) + (size_t)rl * ldk;
-            const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * ldk;
-            int p = h;
-            for (; p + 2 < np; p += 4) { cfma(acc0, own[p], site[p]); cfma(acc1, own[p + 2], site[p + 2]); }
-            for (; p < np; p += 2) cfma(acc0, own[p], site[p]);
-          }
-          cplx acc = cadd(acc0, acc1);
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-          if (act && h == 0) {
-            if (!isB) {
-              cplx v = cadd(gcol[b * rpc * 4 + tt], acc);
-              if (row0 + rl == i + kq * N) v.x -= 1.0;
-              gcc[tt] = v;
-            } else {
-              grc[tt] = cadd(grow[b * rpc * 4 + tt], acc);
-            }
-          }
-        }
-        asm volatile("bar.sync 2, 224;" ::: "memory");
         cplx* Atw = a.At + batch * bufstride;
         cplx* Bmw = a.Bm + batch * bufstride;
         for (int e = t2; e < nown * 8; e += 224) {
@@ -448,7 +443,6 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       kc++;
       np += 4;
     }
-    prev_acc = accepted;
     // ================= flush: G += A B over the pending 4*kc columns =================
     const bool do_flush = (kc == a.kmax || (i == N - 1 && kc > 0));
     if (do_flush) {
@@ -538,7 +532,6 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       batch ^= 1;
       kc = 0;
       np = 0;
-      prev_acc = 0;
       if (have_next) {   // G changed: refresh what was prefetched for site i+1
         fetch_G(i + 1, nb, tid, 256);
         __syncthreads();
