@@ -44,6 +44,10 @@ struct dqmc_ctx {
   // device buffers
   cplx *G, *Gtmp, *u_stack, *t_stack;
   double* d_stack;
+  cplx *gb_G, *gb_u_stack, *gb_t_stack;   // global-update backups (stack.jl:134-143), allocated on first use
+  double *gb_d_stack, *gb_hs;
+  double gb_log_det;
+  double* d_action;                       // [0] result, [1..] per-block partials
   cplx *Ul, *Ur, *Tl, *Tr;
   double *Dl, *Dr;
   cplx* W[5];
@@ -195,6 +199,8 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
   TRY(c, dmalloc(c, &c->d_prof, 32)); c->lu_prof = false;
   TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
+  c->gb_G = c->gb_u_stack = c->gb_t_stack = nullptr; c->gb_d_stack = c->gb_hs = nullptr; c->gb_log_det = 0.0;
+  TRY(c, dmalloc(c, &c->d_action, 1 + 1024));
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
   CU(c, cudaStreamSynchronize(c->st));
@@ -211,7 +217,8 @@ extern "C" int dqmc_destroy(dqmc_ctx* c) {
   void* ptrs[] = {c->G, c->Gtmp, c->u_stack, c->t_stack, c->d_stack, c->Ul, c->Ur, c->Tl, c->Tr, c->Dl, c->Dr,
                   c->W[0], c->W[1], c->W[2], c->W[3], c->W[4], c->tau, c->tfac, c->trsm_work, c->dabs, c->drp_inv,
                   c->colnorm, c->perm, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
-                  c->d_flags, c->d_bar, c->d_logdet, c->d_check};
+                  c->d_flags, c->d_bar, c->d_logdet, c->d_check, c->gb_G, c->gb_u_stack, c->gb_t_stack, c->gb_d_stack,
+                  c->gb_hs, c->d_action};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < F_COUNT; ++i) { if (c->fop[i].idx) cudaFree(c->fop[i].idx); if (c->fop[i].val) cudaFree(c->fop[i].val); }
   cudaStreamDestroy(c->st);
@@ -792,6 +799,130 @@ extern "C" int dqmc_sweep(dqmc_ctx* c, int32_t nupdates, double box, const doubl
     }
   }
   return counters_read(c, consumed, accepted, dS_total);
+}
+
+// ---------------------------------------------------------------------------------------------- boson action / global update
+// calc_boson_action (action.jl:1-52): every (site, slice) adds its forward time difference, its "up" and "right" spatial
+// differences, and its mass / quartic terms; per-block partial sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) boson_action_kernel(const double* __restrict__ hs, const int* __restrict__ nbr, int N, int M,
+                                                           double dtau, double inv_c2, double r, double u, int edrun,
+                                                           double* __restrict__ partial) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const long long tot = (long long)N * M;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % N), s = (int)(e / N);
+    const double* h = hs + 3 * e;
+    const double sq = h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+    double t = dtau * r * 0.5 * sq;
+    if (!edrun) {
+      t += dtau * u * 0.25 * sq * sq;
+      const double* hl = hs + 3 * ((long long)i + (long long)N * ((s + 1) % M));
+      const double* hu = hs + 3 * ((long long)nbr[4 * i + 0] + (long long)N * s);
+      const double* hr = hs + 3 * ((long long)nbr[4 * i + 1] + (long long)N * s);
+      double dt2 = 0.0, ds2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double a = h[k] - hl[k], b = h[k] - hu[k], c = h[k] - hr[k];
+        dt2 += a * a;
+        ds2 += b * b + c * c;
+      }
+      t += 0.5 / dtau * inv_c2 * dt2 + 0.5 * dtau * ds2;
+    }
+    acc += t;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[1 + blockIdx.x] = t;
+  }
+}
+__global__ void boson_action_final_kernel(double* partial, int nblocks) {
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partial[1 + b];
+  partial[0] = t;
+}
+__global__ void shift_field_kernel(double* hs, long long count, double s0, double s1, double s2) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % 3);
+    hs[e] = __dadd_rn(hs[e], k == 0 ? s0 : (k == 1 ? s1 : s2));
+  }
+}
+
+static int boson_action_dev(dqmc_ctx* c, double* out_host) {
+  if (!c->have_nbr) CTX_FAIL(c, "neighbour table not set (dqmc_set_neighbors)");
+  const int nblocks = 256;
+  boson_action_kernel<<<nblocks, 256, 0, c->st>>>(c->hs, c->nbr, c->N, c->M, c->p.delta_tau, 1.0 / (c->p.c * c->p.c), c->p.r,
+                                                  c->p.u, c->p.edrun, c->d_action);
+  boson_action_final_kernel<<<1, 1, 0, c->st>>>(c->d_action, nblocks);
+  CU(c, cudaGetLastError());
+  g_launches += 2;
+  CU(c, cudaMemcpyAsync(out_host, c->d_action, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_calc_boson_action(dqmc_ctx* c, double* S) {
+  CU(c, cudaSetDevice(c->p.device));
+  return boson_action_dev(c, S);
+}
+
+static void global_update_backup_swap(dqmc_ctx* c) {   // global_updates.jl:1-8 (pointer swaps, no copies)
+  std::swap(c->gb_u_stack, c->u_stack);
+  std::swap(c->gb_d_stack, c->d_stack);
+  std::swap(c->gb_t_stack, c->t_stack);
+  std::swap(c->gb_G, c->G);
+}
+
+// global_update (global_updates.jl:18-59).  u[0..2]: shift draws (randuniform(box_global) per component), u[3]: accept draw,
+// consumed only if p_acc <= 1.  S_old = mc.p.boson_action; on acceptance *S_new replaces it.
+extern "C" int dqmc_global_update(dqmc_ctx* c, double box_global, const double* u, double S_old, double* S_new,
+                                  int32_t* accepted, int32_t* consumed) {
+  NEED_OPS(c);
+  CU(c, cudaSetDevice(c->p.device));
+  if (!(c->current_slice == c->M && c->direction == -1))
+    CTX_FAIL(c, "global_update: state must be (slices, -1) (global_updates.jl:22), is (%d, %d)", c->current_slice, c->direction);
+  const size_t n = c->n, nn = n * n, nh = (size_t)3 * c->N * c->M;
+  if (!c->gb_G) {
+    TRY(c, dmalloc(c, &c->gb_G, nn));
+    TRY(c, dmalloc(c, &c->gb_u_stack, nn * c->nel));
+    TRY(c, dmalloc(c, &c->gb_t_stack, nn * c->nel));
+    TRY(c, dmalloc(c, &c->gb_d_stack, n * c->nel));
+    TRY(c, dmalloc(c, &c->gb_hs, nh));
+  }
+  double ld_old = 0.0;
+  CU(c, cudaMemcpyAsync(&ld_old, c->d_logdet, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(c->gb_hs, c->hs, sizeof(double) * nh, cudaMemcpyDeviceToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->gb_log_det = ld_old;
+  global_update_backup_swap(c);
+  const double b2 = 2.0 * box_global;
+  const double s0 = -box_global + b2 * u[0], s1 = -box_global + b2 * u[1], s2 = -box_global + b2 * u[2];
+  shift_field_kernel<<<c->num_sms * 4, 256, 0, c->st>>>(c->hs, (long long)nh, s0, s1, s2);
+  CU(c, cudaGetLastError());
+  g_launches++;
+  TRY(c, dqmc_build_stack(c));
+  TRY(c, propagate_dev(c));
+  double Snew = 0.0, ld_new = 0.0;
+  CU(c, cudaMemcpyAsync(&ld_new, c->d_logdet, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  TRY(c, boson_action_dev(c, &Snew));
+  const double p_acc = exp(-(Snew - S_old)) * exp(ld_old - ld_new);
+  int acc, used = 3;
+  if (p_acc > 1.0) acc = 1;
+  else { acc = u[3] < p_acc; used = 4; }
+  if (!acc) {   // undo the move: field back, stacks / G / logdet swapped back
+    CU(c, cudaMemcpyAsync(c->hs, c->gb_hs, sizeof(double) * nh, cudaMemcpyDeviceToDevice, c->st));
+    global_update_backup_swap(c);
+    CU(c, cudaMemcpyAsync(c->d_logdet, &ld_old, sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  if (S_new) *S_new = acc ? Snew : S_old;
+  if (accepted) *accepted = acc;
+  if (consumed) *consumed = used;
+  return 0;
 }
 
 extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {

@@ -52,6 +52,9 @@ class DQMC:
         self._ctx = C.c_void_p()
         self.boson_action = 0.0
         self.acc_rate = 0.0
+        self.acc_rate_global = 0.0
+        self.acc_global = 0
+        self.prop_global = 0
         cp = _l.DqmcParams(L=p.L, flv=p.flv, opdim=p.opdim, slices=p.slices, safe_mult=p.safe_mult,
                            edrun=int(p.edrun), all_checks=int(p.all_checks), device=device, delay=delay, reserved=0,
                            delta_tau=p.delta_tau, lambda_=p.lambda_, r=p.r, c=p.c, u=p.u)
@@ -237,9 +240,32 @@ class DQMC:
         self.boson_action += dS.value
         return accepted.value / N
 
-    # -- dqmc_framework.jl:500-517 (without global updates) ----------------------------------------------
-    def update(self, stream: UniformStream):
-        self.propagate()
+    # -- global_updates.jl:18-59 -------------------------------------------------------------------------
+    def global_update(self, stream: UniformStream):
+        """Uniform shift of the whole field, full stack rebuild, Metropolis test on exp(-dS) det ratio.  Returns 0/1."""
+        u = stream.take(4)
+        S_new, acc, used = C.c_double(), C.c_int32(), C.c_int32()
+        self._chk(self.lib.dqmc_global_update(self._ctx, self.p.box_global, _l.dptr(u), self.boson_action, C.byref(S_new),
+                                              C.byref(acc), C.byref(used)))
+        stream.advance(used.value)
+        self.boson_action = S_new.value
+        return acc.value
+
+    def device_boson_action(self):
+        v = C.c_double()
+        self._chk(self.lib.dqmc_calc_boson_action(self._ctx, C.byref(v)))
+        return v.value
+
+    # -- dqmc_framework.jl:500-517 -----------------------------------------------------------------------
+    def update(self, stream: UniformStream, i=0):
+        """`update(mc, i)`: propagate, a global update every `global_rate`-th sweep at (slices, -1), local updates."""
+        p = self.p
+        s, d = self.propagate()
+        if p.global_updates and s == p.slices and d == -1 and i % p.global_rate == 0:
+            self.prop_global += 1
+            b = self.global_update(stream)
+            self.acc_rate_global += b
+            self.acc_global += b
         self.acc_rate += self.local_updates(stream)
 
     def sweep(self, stream=None, nupdates=None):

@@ -57,6 +57,8 @@ SIGNATURES = {
     "dqmc_local_updates": (C.c_int, [_P, C.c_double, _D, C.c_int64, _I64, _I64, _D]),
     "dqmc_sweep": (C.c_int, [_P, C.c_int32, C.c_double, _D, C.c_int64, _I64, _I64, _D]),
     "dqmc_set_uniforms": (C.c_int, [_P, _D, C.c_int64]),
+    "dqmc_calc_boson_action": (C.c_int, [_P, _D]),
+    "dqmc_global_update": (C.c_int, [_P, C.c_double, _D, C.c_double, _D, _I32, _I32]),
     "dqmc_timers": (C.c_int, [_P, _D, C.c_int32]),
     "dqmc_set_timing": (C.c_int, [_P, C.c_int32]),
     "dqmc_checks": (C.c_int, [_P, _D, _I64]),

@@ -98,6 +98,14 @@ int dqmc_sweep(dqmc_ctx* ctx, int32_t nupdates, double box, const double* u, int
                int64_t* accepted, double* dS_total);
 int dqmc_set_uniforms(dqmc_ctx* ctx, const double* u, int64_t nu);
 
+/* calc_boson_action (action.jl:1-52) of the device-resident field */
+int dqmc_calc_boson_action(dqmc_ctx* ctx, double* S);
+/* global_update (global_updates.jl:18-59) at (current_slice, direction) == (slices, -1): shift the whole field by
+ * randuniform(box_global) per component (u[0..2]), rebuild the stack, accept with exp(-dS) * exp(logdet_old - logdet_new)
+ * (u[3], consumed only if p_acc <= 1); on rejection stack, G, logdet and field are restored from the backups. */
+int dqmc_global_update(dqmc_ctx* ctx, double box_global, const double* u, double S_old, double* S_new, int32_t* accepted,
+                       int32_t* consumed);
+
 /* telemetry: phase times in ms (CUDA events): [0] wrap, [1] local updates, [2] stack UDT (add_slice_sequence),
  * [3] calculate_greens, [4] total of dqmc_sweep; resets the accumulators.  Replaces the @mytimeit labels
  * (slice_matrices.jl:105-125, local_updates.jl:47,68, stack.jl:256,290,344). */

@@ -401,6 +401,26 @@ class OracleDQMC:
                 self.update_greens(i)
         return acc / self.N
 
+    # ---------------------------------------------------------------- global_updates.jl
+    def global_update(self, rng):
+        """global_updates.jl:18-59 (backup by copy instead of pointer swap).  Returns 0/1."""
+        p = self.p
+        assert self.current_slice == p.slices - 1 and self.direction == -1
+        S_old = self.boson_action
+        bk = (self.u_stack.copy(), self.d_stack.copy(), self.t_stack.copy(), self.greens.copy(), self.log_det, self.hsfield.copy())
+        for k in range(p.opdim):   # global_update_perform_shift! (:10-16)
+            self.hsfield[k] += -p.box_global + 2 * p.box_global * rng.rand()
+        self.build_stack()
+        self.propagate()
+        self.boson_action = self.calc_boson_action()
+        p_acc = np.exp(-(self.boson_action - S_old)) * np.exp(bk[4] - self.log_det)
+        self.last_global_p_acc = float(p_acc)
+        if p_acc > 1.0 or rng.rand() < p_acc:
+            return 1
+        self.boson_action = S_old
+        self.u_stack, self.d_stack, self.t_stack, self.greens, self.log_det, self.hsfield = bk
+        return 0
+
     # ---------------------------------------------------------------- helpers used by the reference's tests
     def calc_greens_fresh(self, slc):
         """fermion_measurements.jl:1061-1101 spirit: G(slice) = [1 + B(slice-1)..B(0)B(M-1)..B(slice)]^-1

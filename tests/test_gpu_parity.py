@@ -229,3 +229,58 @@ def test_large_size_properties(L, M):
     assert maxabs(mc.greens, g_prop) < 1e-9
     assert maxabs(g_first, g_prop) > 1e-6                 # the sweep did change the configuration
     mc.close()
+
+
+# ------------------------------------------------------------------------------------------ boson action / global update
+def test_boson_action_device(golden_o3):
+    # tests_O3.jl:50-59: calc_boson_action(mc, randconf) == 75.57712964980982 (and the edrun value)
+    from dqmc_b200 import DQMC, Params
+    mc, _ = _mk(4, 10, True)
+    mc.hsfield = golden_o3["randconf"]
+    assert np.isclose(mc.device_boson_action(), 75.57712964980982, rtol=1e-13)
+    assert np.isclose(mc.calc_boson_action(golden_o3["randconf"]), 75.57712964980982, rtol=1e-13)
+    mc.close()
+    mce = DQMC(Params(L=4, slices=10, safe_mult=10, Bfield=True, edrun=True), device=0)
+    mce.hsfield = golden_o3["randconf"]
+    assert np.isclose(mce.device_boson_action(), 16.348917129437076, rtol=1e-13)
+    mce.close()
+
+
+@pytest.mark.parametrize("box_global,expect", [(0.02, None), (2.0, 0)])
+def test_global_update_vs_oracle(box_global, expect):
+    # global_updates.jl:18-59: same shift draws -> same new action, log-determinants, decision; reject restores everything
+    from dqmc_b200 import UniformStream
+    L, M = 4, 20
+    mc, om = _mk(L, M, False)
+    mc.p.box_global = box_global
+    om.p.box_global = box_global
+    rs = np.random.RandomState(9)
+    field = rs.rand(3, L * L, M)
+    mc.init(field)
+    om.init(field)
+    g_before, ld_before = mc.greens, mc.log_det
+    assert np.isclose(ld_before, om.log_det, rtol=1e-10)
+    u = rs.rand(8)
+    st, ost = UniformStream(u), OracleStream(u)
+    acc_o = om.global_update(ost)
+    acc = mc.global_update(st)
+    assert acc == acc_o and st.consumed == ost.pos
+    if expect is not None:
+        assert acc == expect
+    assert np.isclose(mc.boson_action, om.boson_action, rtol=1e-12)
+    assert np.array_equal(mc.hsfield, om.hsfield) if acc == 0 else maxabs(mc.hsfield, om.hsfield) < 1e-15
+    assert maxabs(mc.greens, om.greens) < 1e-10
+    assert np.isclose(mc.log_det, om.log_det, rtol=1e-10)
+    assert (mc.current_slice, mc.direction) == (M, -1)
+    if acc == 0:
+        assert maxabs(mc.greens, g_before) == 0.0 and mc.log_det == ld_before
+    # the chain continues consistently after the global move
+    st2, ost2 = UniformStream(rs.rand(4 * L * L * 5)), None
+    ost2 = OracleStream(st2.take(4 * L * L * 5).copy())
+    for _ in range(5):
+        mc.update(st2)
+        om.propagate()
+        om.local_updates(ost2)
+    assert np.array_equal(mc.hsfield, om.hsfield) if acc == 0 else maxabs(mc.hsfield, om.hsfield) < 1e-15
+    assert maxabs(mc.greens, om.greens) < 1e-10
+    mc.close()
