@@ -925,6 +925,74 @@ extern "C" int dqmc_global_update(dqmc_ctx* c, double box_global, const double* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- boson susceptibility
+// measure_chi_dynamic (boson_measurements.jl:6-10, 48-56): chi(qy,qx,iw) = dtau/(N M) sum_k |FT phi_k|^2 on the rfft grid
+// qy, qx in 0..L/2, w in 0..M/2.  Separable DFT: time first (the long axis), then the two short lattice axes.
+__global__ void __launch_bounds__(128) chi_time_dft_kernel(const double* __restrict__ hs, int N, int M, int nt,
+                                                           cplx* __restrict__ F1) {
+  // F1[(k + 3*i)*nt + w] = sum_s phi[k,i,s] exp(-2 pi i s w / M); one block per (k,i) row, threads over w
+  extern __shared__ double row[];
+  const int ki = blockIdx.x;
+  for (int s = threadIdx.x; s < M; s += blockDim.x) row[s] = hs[(size_t)ki + (size_t)3 * N * s];
+  __syncthreads();
+  for (int w = threadIdx.x; w < nt; w += blockDim.x) {
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < M; ++s) {
+      const long long ph = ((long long)s * w) % M;           // exact phase reduction
+      double sn, cs;
+      sincospi(-2.0 * (double)ph / (double)M, &sn, &cs);
+      re = fma(row[s], cs, re);
+      im = fma(row[s], sn, im);
+    }
+    F1[(size_t)ki * nt + w] = cmake(re, im);
+  }
+}
+__global__ void __launch_bounds__(128) chi_space_dft_kernel(const cplx* __restrict__ F1, int L, int nt, int nq, double scale,
+                                                            double* __restrict__ chi) {
+  // chi[qy + nq*(qx + nq*w)] = scale * sum_k | sum_{y,x} F1[k,(y,x),w] exp(-2 pi i (y qy + x qx)/L) |^2
+  const int tot = nq * nq * nt;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < tot; o += gridDim.x * blockDim.x) {
+    const int qy = o % nq, qx = (o / nq) % nq, w = o / (nq * nq);
+    double acc = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      double re = 0.0, im = 0.0;
+      for (int x = 0; x < L; ++x)
+        for (int y = 0; y < L; ++y) {
+          const int ph = (y * qy + x * qx) % L;
+          double sn, cs;
+          sincospi(-2.0 * (double)ph / (double)L, &sn, &cs);
+          const cplx f = F1[(size_t)(k + 3 * (y + L * x)) * nt + w];
+          re += f.x * cs - f.y * sn;
+          im += f.x * sn + f.y * cs;
+        }
+      acc += re * re + im * im;
+    }
+    chi[o] = scale * acc;
+  }
+}
+
+extern "C" int dqmc_measure_chi_dynamic(dqmc_ctx* c, double* chi) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int L = c->p.L, N = c->N, M = c->M, nq = L / 2 + 1, nt = M / 2 + 1;
+  const size_t need = (size_t)3 * N * nt;                       // complex scratch: fits in one n x n work matrix?
+  cplx* F1 = c->W[0];
+  cplx* tmpbuf = nullptr;
+  if (need + (size_t)nq * nq * nt > (size_t)c->n * c->n) {
+    CU(c, cudaMalloc((void**)&tmpbuf, sizeof(cplx) * (need + (size_t)nq * nq * nt)));
+    F1 = tmpbuf;
+  }
+  double* dchi = reinterpret_cast<double*>(F1 + need);
+  chi_time_dft_kernel<<<3 * N, 128, sizeof(double) * M, c->st>>>(c->hs, N, M, nt, F1);
+  chi_space_dft_kernel<<<(nq * nq * nt + 127) / 128, 128, 0, c->st>>>(F1, L, nt, nq, c->p.delta_tau / ((double)N * M), dchi);
+  cudaError_t e = cudaGetLastError();
+  g_launches += 2;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi, dchi, sizeof(double) * nq * nq * nt, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+  if (tmpbuf) cudaFree(tmpbuf);
+  if (e != cudaSuccess) CTX_FAIL(c, "dqmc_measure_chi_dynamic: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {
   CU(c, cudaSetDevice(c->p.device));
   CU(c, cudaStreamSynchronize(c->st));

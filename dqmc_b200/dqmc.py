@@ -251,6 +251,17 @@ class DQMC:
         self.boson_action = S_new.value
         return acc.value
 
+    # -- boson_measurements.jl:6-39 ----------------------------------------------------------------------
+    def measure_chi_dynamic(self):
+        """chi(qy,qx,iw) of the current configuration, shape (L/2+1, L/2+1, M/2+1)."""
+        nq, nt = self.l.L // 2 + 1, self.p.slices // 2 + 1
+        chi = np.zeros((nq, nq, nt), order="F")
+        self._chk(self.lib.dqmc_measure_chi_dynamic(self._ctx, _l.dptr(chi)))
+        return chi
+
+    def measure_chi_static(self):
+        return float(self.measure_chi_dynamic()[0, 0, 0])
+
     def device_boson_action(self):
         v = C.c_double()
         self._chk(self.lib.dqmc_calc_boson_action(self._ctx, C.byref(v)))

@@ -58,6 +58,7 @@ SIGNATURES = {
     "dqmc_sweep": (C.c_int, [_P, C.c_int32, C.c_double, _D, C.c_int64, _I64, _I64, _D]),
     "dqmc_set_uniforms": (C.c_int, [_P, _D, C.c_int64]),
     "dqmc_calc_boson_action": (C.c_int, [_P, _D]),
+    "dqmc_measure_chi_dynamic": (C.c_int, [_P, _D]),
     "dqmc_global_update": (C.c_int, [_P, C.c_double, _D, C.c_double, _D, _I32, _I32]),
     "dqmc_timers": (C.c_int, [_P, _D, C.c_int32]),
     "dqmc_set_timing": (C.c_int, [_P, C.c_int32]),

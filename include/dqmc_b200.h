@@ -100,6 +100,9 @@ int dqmc_set_uniforms(dqmc_ctx* ctx, const double* u, int64_t nu);
 
 /* calc_boson_action (action.jl:1-52) of the device-resident field */
 int dqmc_calc_boson_action(dqmc_ctx* ctx, double* S);
+/* measure_chi_dynamic (boson_measurements.jl:6-10,48-56) of the device-resident field: chi[qy,qx,w], column-major,
+ * (L/2+1) x (L/2+1) x (M/2+1) Float64 */
+int dqmc_measure_chi_dynamic(dqmc_ctx* ctx, double* chi);
 /* global_update (global_updates.jl:18-59) at (current_slice, direction) == (slices, -1): shift the whole field by
  * randuniform(box_global) per component (u[0..2]), rebuild the stack, accept with exp(-dS) * exp(logdet_old - logdet_new)
  * (u[3], consumed only if p_acc <= 1); on rejection stack, G, logdet and field are restored from the backups. */

@@ -401,6 +401,19 @@ class OracleDQMC:
                 self.update_greens(i)
         return acc / self.N
 
+    # ---------------------------------------------------------------- boson_measurements.jl
+    def measure_chi_dynamic(self, conf=None):
+        """boson_measurements.jl:6-10, 48-56: dtau/(N M) * sum_k |rfft(phi_k)|^2 restricted to [:, 1:n, 1:nt]."""
+        p = self.p
+        conf = self.hsfield if conf is None else conf
+        opdim, sites, slices = conf.shape
+        L = int(round(np.sqrt(sites)))
+        h = conf.reshape(opdim, L, L, slices, order="F")
+        ft = np.fft.fftn(h, axes=(1, 2, 3))
+        n, nt = L // 2 + 1, slices // 2 + 1
+        C = np.sum(np.abs(ft) ** 2, axis=0)[:n, :n, :nt]
+        return p.delta_tau / (sites * slices) * C
+
     # ---------------------------------------------------------------- global_updates.jl
     def global_update(self, rng):
         """global_updates.jl:18-59 (backup by copy instead of pointer swap).  Returns 0/1."""

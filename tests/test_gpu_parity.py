@@ -284,3 +284,19 @@ def test_global_update_vs_oracle(box_global, expect):
     assert np.array_equal(mc.hsfield, om.hsfield) if acc == 0 else maxabs(mc.hsfield, om.hsfield) < 1e-15
     assert maxabs(mc.greens, om.greens) < 1e-10
     mc.close()
+
+
+def test_chi_dynamic_device(golden_o3):
+    # tests_O3_measurements.jl:1-6: chi(q, iw) of randconf vs the chi_dyn fixture and chi_static == 12.420575691388407
+    mc, om = _mk(4, 10, True)
+    mc.hsfield = golden_o3["randconf"]
+    chi = mc.measure_chi_dynamic()
+    assert maxabs(chi, golden_o3["chi_dyn"]) < 1e-12
+    assert np.isclose(mc.measure_chi_static(), 12.420575691388407, rtol=1e-12)
+    mc.close()
+    mc, om = _mk(8, 40, False)
+    f = np.random.RandomState(4).rand(3, 64, 40)
+    mc.hsfield = f
+    ref = om.measure_chi_dynamic(f)
+    assert np.max(np.abs(mc.measure_chi_dynamic() - ref) / (1e-300 + np.abs(ref).max())) < 1e-12
+    mc.close()

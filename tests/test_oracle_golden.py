@@ -229,3 +229,10 @@ def test_decompose_udt_properties(golden_linalg):
     u, d, t = decompose_udt(mat)
     assert np.isclose(d.max(), 5.8846316709257896e16, rtol=1e-9)
     assert np.isclose(d.min(), 1.9123571535539083e-24, rtol=1e-6)
+
+
+def test_chi_dynamic(mc_b, golden_o3):
+    # tests_O3_measurements.jl:1-6
+    chi = mc_b.measure_chi_dynamic(golden_o3["randconf"])
+    assert maxabs(chi, golden_o3["chi_dyn"]) < 1e-12
+    assert np.isclose(chi[0, 0, 0], 12.420575691388407, rtol=1e-13)
