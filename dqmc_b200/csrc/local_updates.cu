@@ -167,12 +167,13 @@ __device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, const
 __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.n, N = a.nsites, ldk = 4 * a.kmax, rpc = a.rpc;
+  const int lds = ldk + 2;                                  // shared-memory row stride: +2 spreads the 4 rows of a site over the banks
   const size_t bufstride = (size_t)ldk * n;                 // one At / Bm buffer
   cplx* sp = reinterpret_cast<cplx*>(smem_raw);
-  cplx* Aown = sp; sp += (size_t)rpc * ldk;                 // [rpc][ldk] my rows of A
-  cplx* Bown = sp; sp += (size_t)rpc * ldk;                 // [rpc][ldk] my columns of B
-  cplx* As4 = sp; sp += 2 * 4 * ldk;                        // [2][4][ldk] rows site+kN of A (double-buffered by site parity)
-  cplx* Bs4 = sp; sp += 2 * 4 * ldk;                        // [2][4][ldk] cols site+kN of B
+  cplx* Aown = sp; sp += (size_t)rpc * lds;                 // [rpc][ldk] my rows of A
+  cplx* Bown = sp; sp += (size_t)rpc * lds;                 // [rpc][ldk] my columns of B
+  cplx* As4 = sp; sp += 2 * 4 * lds;                        // [2][4][ldk] rows site+kN of A (double-buffered by site parity)
+  cplx* Bs4 = sp; sp += 2 * 4 * lds;                        // [2][4][ldk] cols site+kN of B
   cplx* gcol = sp; sp += (size_t)2 * rpc * 4;               // [2][rpc][4] G[r, site+kN] for my rows
   cplx* grow = sp; sp += (size_t)2 * rpc * 4;               // [2][rpc][4] G[site+kN, c] for my cols
   cplx* FA = sp; sp += 64 * 36;                             // flush staging: 64 rows x 32 k (+4 pad)
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       {
         const int w8 = (tp >> 2) & 1, k8 = tp & 3, p8 = tp >> 3;
         const cplx* sbase = (w8 ? Bmb : Atb) + (size_t)(i + 1 + k8 * N) * ldk;
-        cplx* dbase = (w8 ? Bs4 : As4) + (nb * 4 + k8) * ldk;
+        cplx* dbase = (w8 ? Bs4 : As4) + (nb * 4 + k8) * lds;
         unsigned long long vx[8], vy[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -330,9 +331,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         const int o = tp >> 1, h = tp & 1, which = o >> 4, idx = o & 15;
         const cplx *pa, *pb;
         cplx base;
-        if (which == 0) { pa = As4 + (nb * 4 + (idx & 3)) * ldk; pb = Bs4 + (nb * 4 + (idx >> 2)) * ldk; base = g4r[idx]; }
-        else if (which == 1) { pa = As4 + (nb * 4 + (idx >> 2)) * ldk; pb = Bs4 + (b * 4 + (idx & 3)) * ldk; base = Gx1[idx]; }
-        else { pa = As4 + (b * 4 + (idx >> 2)) * ldk; pb = Bs4 + (nb * 4 + (idx & 3)) * ldk; base = Gx2[idx]; }
+        if (which == 0) { pa = As4 + (nb * 4 + (idx & 3)) * lds; pb = Bs4 + (nb * 4 + (idx >> 2)) * lds; base = g4r[idx]; }
+        else if (which == 1) { pa = As4 + (nb * 4 + (idx >> 2)) * lds; pb = Bs4 + (b * 4 + (idx & 3)) * lds; base = Gx1[idx]; }
+        else { pa = As4 + (b * 4 + (idx >> 2)) * lds; pb = Bs4 + (nb * 4 + (idx & 3)) * lds; base = Gx2[idx]; }
         cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
         int p = h;
         for (; p + 2 < np; p += 4) { cfma(acc0, pa[p], pb[p]); cfma(acc1, pa[p + 2], pb[p + 2]); }
@@ -358,8 +359,8 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         const int rl = tt >> 2, kq = tt & 3;
         cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
         if (act) {
-          const cplx* own = (isB ? Bown : Aown) + (size_t)rl * ldk;
-          const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * ldk;
+          const cplx* own = (isB ? Bown : Aown) + (size_t)rl * lds;
+          const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * lds;
           int p = h;
           for (; p + 2 < np; p += 4) { cfma(acc0, own[p], site[p]); cfma(acc1, own[p + 2], site[p + 2]); }
           for (; p < np; p += 2) cfma(acc0, own[p], site[p]);
@@ -406,8 +407,8 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           }
           // T1 = rows i+1+rN of the new A columns, T2 = columns i+1+cN of the new B rows: the next site's copies are
           // complete without a round trip through memory
-          if (lane < 16) As4[(nb * 4 + r) * ldk + np + c] = acc;
-          else Bs4[(nb * 4 + c) * ldk + np + r] = acc;
+          if (lane < 16) As4[(nb * 4 + r) * lds + np + c] = acc;
+          else Bs4[(nb * 4 + c) * lds + np + r] = acc;
           __syncwarp();
           if (lane < 16) {
             const int rr = lane & 3, cc = lane >> 2;       // g4e layout [r + 4c]
@@ -430,12 +431,12 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           if (!isB) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) cfma(acc, gcc[rl * 4 + kk], Minv[kk * 4 + kq]);
-            Aown[(size_t)rl * ldk + np + kq] = acc;
+            Aown[(size_t)rl * lds + np + kq] = acc;
             st_pub(Atw + (size_t)(row0 + rl) * ldk + np + kq, acc);
           } else {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[kq * 4 + kk], grc[rl * 4 + kk]);
-            Bown[(size_t)rl * ldk + np + kq] = acc;
+            Bown[(size_t)rl * lds + np + kq] = acc;
             st_pub(Bmw + (size_t)(row0 + rl) * ldk + np + kq, acc);
           }
         }
@@ -578,7 +579,8 @@ int local_updates_grid(int n, int num_sms, int* rpc) {
 
 size_t local_updates_smem(const LUArgs& a) {
   const int ldk = 4 * a.kmax;
-  return sizeof(cplx) * ((size_t)2 * a.rpc * ldk + 16 * ldk + 16 * a.rpc + 2 * 64 * 36) + sizeof(double) * 10 * a.nsites +
+  const int lds = ldk + 2;
+  return sizeof(cplx) * ((size_t)2 * a.rpc * lds + 16 * lds + 16 * a.rpc + 2 * 64 * 36) + sizeof(double) * 10 * a.nsites +
          sizeof(int) * 4 * a.nsites;
 }
 

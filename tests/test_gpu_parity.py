@@ -201,7 +201,7 @@ def test_sweep_vs_oracle_shared_stream(L, M, delay):
 
 
 # ------------------------------------------------------------------------------------------ BASELINE sizes: properties
-@pytest.mark.parametrize("L,M", [(12, 40), (16, 40)])
+@pytest.mark.parametrize("L,M", [(12, 40), (16, 40), (20, 20)])
 def test_large_size_properties(L, M):
     from dqmc_b200 import UniformStream
     mc, _ = _mk(L, M, False)
