@@ -1102,6 +1102,19 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
         rc = run_chain(c, false, c->W[4], ch, nullptr, c->colnorm);
         break;
       }
+      case 8:    // QR only (W[1] <- W[4], factor)
+        rc = cudaMemcpyAsync(c->W[1], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
+        if (!rc) rc = qr_factor(c->st, c->W[1], n, n, c->tau, c->dabs, c->tfac, nullptr, 0, 0, c->num_sms, c->lookahead ? &c->qra : nullptr);
+        break;
+      case 9: rc = qr_form_q(c->st, c->W[1], n, n, c->tfac, c->W[3], n, c->num_sms); break;
+      case 10:   // the serial panel chain alone (no trailing updates): lower bound of the QR critical path
+        rc = qr_panels_only(c->st, c->W[1], n, n, c->tau, c->dabs, c->tfac);
+        break;
+      case 11: rc = trsm_upper(c->st, c->W[1], n, n, c->W[3], n, n, c->trsm_work, nullptr, c->num_sms); break;
+      case 12:   // QR with Q^H applied to n right-hand sides (the calculate_greens shape)
+        rc = cudaMemcpyAsync(c->W[1], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
+        if (!rc) rc = qr_factor(c->st, c->W[1], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms, c->lookahead ? &c->qra : nullptr);
+        break;
       default: rc = -1; snprintf(g_errbuf, sizeof(g_errbuf), "dqmc_bench_kernel: unknown kernel %d", which);
     }
   }

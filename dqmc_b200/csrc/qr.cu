@@ -3,16 +3,49 @@
 namespace cg = cooperative_groups;
 
 // =====================================================================================================
-// Panel factorization: one thread-block cluster of QR_CL CTAs; each CTA keeps a slab of rows of the
-// m x nb panel in shared memory (row-major, 32 columns per row, padded to 33).  Thread (c, g) owns column c
-// on the rows {g, g+8, ...} of the slab.  Per column ONE cluster barrier: every CTA reduces the dot products
-// of the current column with all other panel columns over its rows (rows below the diagonal only) and pushes
-// them, plus row j if it owns it, into every CTA's shared memory (distributed shared memory stores).  After the
-// barrier every CTA derives beta, tau, v and the update coefficients redundantly from local data.  The dots with
-// the already-finished columns give V^H v_j, i.e. the compact-WY T factor, for free.
+// Panel factorization: one thread-block cluster of QR_CL CTAs; each CTA owns a slab of rows of the m x nb
+// panel and keeps it in REGISTERS: thread (c = lane, g = warp) holds column c on the local rows {g + NW*t}.
+// The rows of column j that warp g needs are exactly the ones lane j of the same warp holds, so the current
+// column travels through a per-warp shared-memory line (one predicated store, broadcast loads, __syncwarp) and
+// the slab itself is never re-read from shared memory (the earlier shared-memory-resident version was bound by
+// 3 passes x 64 KB of shared-memory traffic per column).  Per column ONE cluster barrier: every CTA reduces the
+// dot products of the current column with all panel columns over its rows (rows below the diagonal only) and
+// pushes them, plus row j if it owns it, into every CTA's shared memory (distributed shared memory stores).
+// After the barrier every CTA derives beta, tau, v and the update coefficients redundantly from local data.
+// The dots with the already-finished columns give V^H v_j, i.e. the compact-WY T factor, for free.
 // =====================================================================================================
 #define QR_LDA 33
-__global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(256)
+#define QR_TX_BYTES ((QR_CL + 1) * QR_NB * 16)   // per column and CTA: QR_CL partial-dot vectors + row j
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 16-byte store into the shared memory of another CTA of the cluster, counted on that CTA's transaction barrier
+__device__ __forceinline__ void st_async_c16(uint32_t raddr, cplx v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "d"(v.x), "d"(v.y), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+#ifdef QRV_ACQ
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+#endif
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int NW, int T>
+__global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(NW * 32)
 qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
                 double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
   cg::cluster_group cl = cg::this_cluster();
@@ -25,171 +58,213 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
   const int tid = threadIdx.x, g = tid >> 5, c = tid & 31;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // a[rl*QR_LDA + c]
-  __shared__ cplx part[8][QR_NB];                // per-warp partial dots
+  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // staging for the coalesced load / store: a[rl*QR_LDA + c]
+  __shared__ cplx part[NW][QR_NB];               // per-warp partial dots
+  __shared__ cplx colbuf[NW][T];                 // current column on the rows of warp g (zero on rows <= j)
+  __shared__ cplx rowl[QR_NB];                   // row j of the panel (owner CTA only)
   __shared__ cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][column]: partial dots of every CTA
   __shared__ cplx rowv[2][QR_NB];                // [parity][column]: row j of the panel (pushed by its owner)
-  __shared__ cplx Tsm[QR_NB][QR_NB + 1];
-  __shared__ cplx gsm[QR_NB];
-  __shared__ cplx tpart[8][QR_NB];
+  __shared__ cplx Tsm[QR_NB][QR_NB + 1];         // rank 0: compact-WY T; rows {g, g+8, g+16, g+24} belong to warp g
+  __shared__ cplx gsm[8][QR_NB];                 // V^H v_j, one private copy per warp (no CTA barrier between write and use)
   __shared__ cplx tau_s[QR_NB];
   __shared__ double beta_s[QR_NB];
+  __shared__ __align__(8) unsigned long long full[2];   // transaction barriers, one per parity
 
   // global -> shared: consecutive threads along rows (coalesced), 32 columns
-  for (int e = tid; e < nloc * QR_NB; e += blockDim.x) {
+  for (int e = tid; e < nloc * QR_NB; e += NW * 32) {
     const int rl = e % nloc, cc = e / nloc;
     a[rl * QR_LDA + cc] = cc < nb ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
   }
   if (rank == 0)
-    for (int e = tid; e < QR_NB * (QR_NB + 1); e += blockDim.x) (&Tsm[0][0])[e] = cmake(0.0, 0.0);
+    for (int e = tid; e < QR_NB * (QR_NB + 1); e += NW * 32) (&Tsm[0][0])[e] = cmake(0.0, 0.0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  cplx x[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int rl = g + NW * t;
+    x[t] = rl < nloc ? a[rl * QR_LDA + c] : cmake(0.0, 0.0);
+  }
+  if (c == 0) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) colbuf[g][t] = (r_begin + g + NW * t > 0) ? x[t] : cmake(0.0, 0.0);
+  }
+  // remote addresses of my slots in CTA g's exchange buffers (warp g pushes to CTA g)
+  const uint32_t dst_rank = (uint32_t)(g < QR_CL ? g : 0);
+  const uint32_t r_xch = mapa_u32(smem_u32(&xch[0][rank][c]), dst_rank);
+  const uint32_t r_row = mapa_u32(smem_u32(&rowv[0][c]), dst_rank);
+  const uint32_t r_bar = mapa_u32(smem_u32(&full[0]), dst_rank);
+  const uint32_t l_bar = smem_u32(&full[0]);
+  cl.sync();   // every CTA's barriers are initialised before anybody stores into them
 
+  cplx tau_prev = cmake(0.0, 0.0);
   for (int j = 0; j < nb; ++j) {
     const int par = j & 1;
-    // ---- phase A: t_c = sum_{r>j} conj(a[r][j]) a[r][c] over my rows (4 independent accumulators)
+    const int jl = j - r_begin;                  // local index of row j (owner CTA: 0 <= jl < nloc)
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar + 8 * par), "r"(QR_TX_BYTES) : "memory");
+    // ---- phase A: t_c = sum_{r>j} conj(a[r][j]) a[r][c] over my rows
+    cplx d[T];
     {
       cplx acc0 = cmake(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-      int rl = g;
-      // rows are visited in increasing order; skip those with r <= j
-      const int first = j + 1 - r_begin;                    // first local row with r > j
-      if (first > rl) rl += ((first - rl + 7) / 8) * 8;
-      for (; rl + 24 < nloc; rl += 32) {
-        cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
-        cfma_conj(acc1, a[(rl + 8) * QR_LDA + j], a[(rl + 8) * QR_LDA + c]);
-        cfma_conj(acc2, a[(rl + 16) * QR_LDA + j], a[(rl + 16) * QR_LDA + c]);
-        cfma_conj(acc3, a[(rl + 24) * QR_LDA + j], a[(rl + 24) * QR_LDA + c]);
+#pragma unroll
+      for (int t = 0; t < T; ++t) d[t] = colbuf[g][t];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if ((t & 3) == 0) cfma_conj(acc0, d[t], x[t]);
+        else if ((t & 3) == 1) cfma_conj(acc1, d[t], x[t]);
+        else if ((t & 3) == 2) cfma_conj(acc2, d[t], x[t]);
+        else cfma_conj(acc3, d[t], x[t]);
       }
-      for (; rl < nloc; rl += 8) cfma_conj(acc0, a[rl * QR_LDA + j], a[rl * QR_LDA + c]);
       part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (g + NW * t == jl) rowl[c] = x[t];
     }
     PSTAMP(0);
-    if (rank == 0 && j > 0) {
-      // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise), computed
-      // in the shadow of this column's dot products; thread (i = c, k = g mod 8)
-      const int jp = j - 1;
-      cplx acc = cmake(0.0, 0.0);
-      if (c < jp)
-        for (int k = c + ((g - c) & 7); k < jp; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
-      tpart[g][c] = acc;
-    }
     __syncthreads();
-    {
-      // every warp g sums the 8 partials of column c and pushes the result to CTA g of the cluster
-      cplx t = part[0][c];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) t = cadd(t, part[w][c]);
-      cplx* dst = cl.map_shared_rank(&xch[0][0][0], g);
-      dst[(par * QR_CL + rank) * QR_NB + c] = t;
-      const int owner = j / rs;
-      if (rank == owner) {
-        cplx* dr = cl.map_shared_rank(&rowv[0][0], g);
-        dr[par * QR_NB + c] = a[(j - r_begin) * QR_LDA + c];
+    if (g < QR_CL) {
+      // warp g sums the NW partials of column c and pushes the result (and row j, if mine) to CTA g of the cluster
+      cplx p0 = cadd(part[0][c], part[1][c]), p1 = cadd(part[2][c], part[3][c]);
+      cplx p2 = cadd(part[4][c], part[5][c]), p3 = cadd(part[6][c], part[7][c]);
+      if (NW > 8) {
+        p0 = cadd(p0, cadd(part[8 % NW][c], part[9 % NW][c])); p1 = cadd(p1, cadd(part[10 % NW][c], part[11 % NW][c]));
+        p2 = cadd(p2, cadd(part[12 % NW][c], part[13 % NW][c])); p3 = cadd(p3, cadd(part[14 % NW][c], part[15 % NW][c]));
       }
-      if (rank == 0 && j > 0 && g == 1) {
-        const int jp = j - 1;
-        if (c < jp) {
-          cplx tt = tpart[0][c];
-#pragma unroll
-          for (int w = 1; w < 8; ++w) tt = cadd(tt, tpart[w][c]);
-          Tsm[c][jp] = cneg(cmul(tau_s[jp], tt));
-        } else if (c == jp) {
-          Tsm[jp][jp] = tau_s[jp];
-        }
-      }
+      st_async_c16(r_xch + par * (QR_CL * QR_NB * 16), cadd(cadd(p0, p1), cadd(p2, p3)), r_bar + 8 * par);
+      if (jl >= 0 && jl < nloc) st_async_c16(r_row + par * (QR_NB * 16), rowl[c], r_bar + 8 * par);
     }
     PSTAMP(1);
-    cl.sync();
-    // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
-    cplx tc = xch[par][0][c], tj = xch[par][0][j];
-    if (prof) { if (tc.x == 1.2345e300) pc[5]++; }
-    PSTAMP(2);
+    if (rank == 0 && j > 0 && g < 8) {
+      // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise) in the
+      // shadow of the exchange: warp g owns rows i = g + 8q; lane = (q, h) sums k = h, h+8, ... and the 8 h-lanes combine
+      const int jp = j - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
+      cplx acc = cmake(0.0, 0.0);
+      if (i < jp) {
 #pragma unroll
-    for (int src = 1; src < QR_CL; ++src) { tc = cadd(tc, xch[par][src][c]); tj = cadd(tj, xch[par][src][j]); }
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = h + 8 * kk;
+          if (k >= i && k < jp) cfma(acc, Tsm[i][k], gsm[g][k]);
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (h == 0) {
+        if (i < jp) Tsm[i][jp] = cneg(cmul(tau_prev, acc));
+        else if (i == jp) Tsm[jp][jp] = tau_prev;
+      }
+      __syncwarp();
+    }
+    mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
+    // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
+    PSTAMP(2);
+    cplx tc, tj;
+    {
+      const cplx c0 = cadd(xch[par][0][c], xch[par][1][c]), c1 = cadd(xch[par][2][c], xch[par][3][c]);
+      const cplx c2 = cadd(xch[par][4][c], xch[par][5][c]), c3 = cadd(xch[par][6][c], xch[par][7][c]);
+      const double j0 = xch[par][0][j].x + xch[par][1][j].x, j1 = xch[par][2][j].x + xch[par][3][j].x;
+      const double j2 = xch[par][4][j].x + xch[par][5][j].x, j3 = xch[par][6][j].x + xch[par][7][j].x;
+      tc = cadd(cadd(c0, c1), cadd(c2, c3));
+      tj = cmake((j0 + j1) + (j2 + j3), 0.0);
+    }
     const cplx alpha = rowv[par][j], rowc = rowv[par][c];
-    const double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + tj.x);
+    const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double nrm2 = aa + tj.x;
     double beta;
     cplx tau, scale;
-    if (nrm == 0.0) {
+    if (nrm2 == 0.0) {
       beta = 0.0; tau = cmake(0.0, 0.0); scale = cmake(0.0, 0.0);
     } else {
+      const double nrm = sqrt(nrm2);
       beta = alpha.x >= 0.0 ? -nrm : nrm;
+      // |alpha - beta|^2 = 2 |alpha|^2 + t_j + 2 |Re alpha| nrm: independent of the division that gives 1/beta
+      const double id = 1.0 / (aa + nrm2 + 2.0 * fabs(alpha.x) * nrm);
       const double ib = 1.0 / beta;
+      const double ar = alpha.x - beta;
       tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
-      const double ar = alpha.x - beta, id = 1.0 / (ar * ar + alpha.y * alpha.y);
       scale = cmake(ar * id, -alpha.y * id);
     }
     // w_c = conj(tau) * v^H a_c = conj(tau) * (a[j][c] + conj(scale) * t_c)      (c > j)
     cplx wc = rowc;
     cfma(wc, cconj(scale), tc);
     wc = cmul(cconj(tau), wc);
-    if (rank == 0 && g == 0) {
+    if (rank == 0 && g < 8) {
       // g_c = V_c^H v_j = conj(V[j][c]) + scale * conj(t_c)   (c < j)
       cplx gg = cconj(rowc);
       cfma(gg, scale, cconj(tc));
-      gsm[c] = c < j ? gg : cmake(0.0, 0.0);
-      if (c == 0) { tau_s[j] = tau; beta_s[j] = beta; }
+      gsm[g][c] = c < j ? gg : cmake(0.0, 0.0);
+      if (tid == 0) { tau_s[j] = tau; beta_s[j] = beta; }
     }
+    tau_prev = tau;
     PSTAMP(3);
-    // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j); column j <- v (below the diagonal) and beta (diagonal)
+    // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j) with v_r = scale * a[r][j] (r > j), v_j = 1;
+    //      column j <- v below the diagonal and beta on it.  One multiply-add per element: x <- s + d * q.
     {
-      int rl0 = g;
-      const int first = j - r_begin;                        // first local row with r >= j
-      if (first > rl0) rl0 += ((first - rl0 + 7) / 8) * 8;
-      if (c > j) {
-        int rl = rl0;
-        for (; rl + 24 < nloc; rl += 32) {
-          cplx x0 = a[rl * QR_LDA + j], x1 = a[(rl + 8) * QR_LDA + j], x2 = a[(rl + 16) * QR_LDA + j], x3 = a[(rl + 24) * QR_LDA + j];
-          cplx t0 = a[rl * QR_LDA + c], t1 = a[(rl + 8) * QR_LDA + c], t2 = a[(rl + 16) * QR_LDA + c], t3 = a[(rl + 24) * QR_LDA + c];
-          x0 = (r_begin + rl == j) ? cmake(1.0, 0.0) : cmul(x0, scale);
-          x1 = cmul(x1, scale); x2 = cmul(x2, scale); x3 = cmul(x3, scale);
-          a[rl * QR_LDA + c] = csub(t0, cmul(x0, wc));
-          a[(rl + 8) * QR_LDA + c] = csub(t1, cmul(x1, wc));
-          a[(rl + 16) * QR_LDA + c] = csub(t2, cmul(x2, wc));
-          a[(rl + 24) * QR_LDA + c] = csub(t3, cmul(x3, wc));
-        }
-        for (; rl < nloc; rl += 8) {
-          cplx x0 = a[rl * QR_LDA + j];
-          x0 = (r_begin + rl == j) ? cmake(1.0, 0.0) : cmul(x0, scale);
-          a[rl * QR_LDA + c] = csub(a[rl * QR_LDA + c], cmul(x0, wc));
+      const cplx q = (c == j) ? scale : (c > j ? cneg(cmul(scale, wc)) : cmake(0.0, 0.0));
+      const cplx pv = (c == j) ? cmake(beta, 0.0) : wc;
+      if (NW > 8) {   // 512-thread variant: 128 registers per thread, so the column is re-read instead of kept
+#pragma unroll
+        for (int t = 0; t < T; ++t) d[t] = colbuf[g][t];
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int r = r_begin + g + NW * t;
+        cplx s = (c == j && r > j) ? cmake(0.0, 0.0) : x[t];
+        cfma(s, d[t], q);
+        if (r == j && c >= j) s = (c == j) ? pv : csub(s, pv);
+        x[t] = s;
+      }
+      if (c == j + 1) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int rl = g + NW * t;
+          colbuf[g][t] = (r_begin + rl > j + 1 && rl < nloc) ? x[t] : cmake(0.0, 0.0);
         }
       }
       __syncwarp();
-      // column j itself: lane l of warp g rewrites row rl0 + 8*l (every row of the slab belongs to exactly one warp)
-      for (int rl = rl0 + 8 * c; rl < nloc; rl += 8 * 32) {
-        const int r = r_begin + rl;
-        a[rl * QR_LDA + j] = (r == j) ? cmake(beta, 0.0) : cmul(a[rl * QR_LDA + j], scale);
-      }
     }
     PSTAMP(4);
-    __syncthreads();
   }
   if (prof && rank == 0 && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
-  if (rank == 0) {   // T column of the last reflector
-    const int jp = nb - 1;
+  if (rank == 0 && g < 8) {   // T column of the last reflector
+    const int jp = nb - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
     cplx acc = cmake(0.0, 0.0);
-    if (c < jp)
-      for (int k = c + ((g - c) & 7); k < jp; k += 8) cfma(acc, Tsm[c][k], gsm[k]);
-    tpart[g][c] = acc;
-    __syncthreads();
-    if (g == 0) {
-      if (c < jp) {
-        cplx tt = tpart[0][c];
+    if (i < jp) {
 #pragma unroll
-        for (int w = 1; w < 8; ++w) tt = cadd(tt, tpart[w][c]);
-        Tsm[c][jp] = cneg(cmul(tau_s[jp], tt));
-      } else if (c == jp) {
-        Tsm[jp][jp] = tau_s[jp];
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = h + 8 * kk;
+        if (k >= i && k < jp) cfma(acc, Tsm[i][k], gsm[g][k]);
       }
     }
-    __syncthreads();
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (h == 0) {
+      if (i < jp) Tsm[i][jp] = cneg(cmul(tau_prev, acc));
+      else if (i == jp) Tsm[jp][jp] = tau_prev;
+    }
   }
-
-  for (int e = tid; e < nloc * nb; e += blockDim.x) {
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int rl = g + NW * t;
+    if (rl < nloc) a[rl * QR_LDA + c] = x[t];
+  }
+  __syncthreads();
+  for (int e = tid; e < nloc * nb; e += NW * 32) {
     const int rl = e % nloc, cc = e / nloc;
     A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
   }
   if (rank == 0) {
-    for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) {
+    for (int e = tid; e < QR_NB * QR_NB; e += NW * 32) {
       int i = e % QR_NB, k = e / QR_NB;
       Tout[e] = (i < nb && k < nb) ? Tsm[i][k] : cmake(0.0, 0.0);
     }
@@ -324,16 +399,30 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
 }
 
 long long* g_qr_prof = nullptr;
-static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
-  const int rs = (m + QR_CL - 1) / QR_CL;
-  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * rs + 8);
+template <int NW, int T>
+static int launch_panel_t(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* Tf, size_t smem) {
   static size_t smem_lim = 0;
-  if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel, &smem_lim)) return -1;
+  if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel<NW, T>, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
-  qr_panel_kernel<<<QR_CL, 256, smem, st>>>(A, lda, m, nb, tau, dabs, T, g_qr_prof);
+  qr_panel_kernel<NW, T><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, g_qr_prof);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
+}
+static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
+  const int rs = (m + QR_CL - 1) / QR_CL;
+  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * rs + 8);
+  if (rs <= 8) return launch_panel_t<8, 1>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 16) return launch_panel_t<8, 2>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 32) return launch_panel_t<8, 4>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 64) return launch_panel_t<8, 8>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 96) return launch_panel_t<8, 12>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 128) return launch_panel_t<8, 16>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 160) return launch_panel_t<16, 10>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 208) return launch_panel_t<16, 13>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 256) return launch_panel_t<16, 16>(st, A, lda, m, nb, tau, dabs, T, smem);
+  snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m);
+  return -1;
 }
 
 static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cplx* T, int conjT, cplx* C, int ldc,
@@ -373,6 +462,13 @@ int qr_factor(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs,
     CUDA_TRY(cudaEventRecord(as->eB, as->st2));
   }
   if (la) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
+  return 0;
+}
+
+int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac) {
+  for (int j0 = 0, k = 0; j0 < n; j0 += QR_NB, ++k)
+    if (launch_panel(st, A + (size_t)j0 * lda + j0, lda, n - j0, min(QR_NB, n - j0), tau + j0, dabs + j0, tfac + (size_t)k * QR_NB * QR_NB))
+      return -1;
   return 0;
 }
 

@@ -24,3 +24,5 @@ int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, 
 // X = R^{-1} Y in place in Y (n x nrhs); R = upper triangle of A.  work: ceil(n/32)*1024 cplx.
 int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
                const double* rowscale, int num_sms);
+// bench hook: the panel factorizations of qr_factor without any trailing update
+int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac);
