@@ -44,45 +44,33 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-template <int NW, int T>
-__global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(NW * 32)
-qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
-                double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
-  cg::cluster_group cl = cg::this_cluster();
+// Shared-memory state of one CTA of the panel cluster (static part)
+template <int NW>
+struct PanelSmem {
+  cplx part[NW][QR_NB];               // per-warp partial dots
+  cplx colbuf[NW][20];                // current column on the rows of warp g (zero on rows <= j)
+  cplx rowl[QR_NB];                   // row j of the panel (rank 0)
+  cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][column]: partial dots of every CTA
+  cplx rowv[2][QR_NB];                // [parity][column]: row j of the panel (pushed by rank 0)
+  cplx Tsm[QR_NB][QR_NB + 1];         // rank 0: compact-WY T; rows {g, g+8, g+16, g+24} belong to warp g
+  cplx gsm[8][QR_NB];                 // V^H v_j, one private copy per warp (no CTA barrier between write and use)
+  cplx tau_s[QR_NB];
+  double beta_s[QR_NB];
+  unsigned long long full[2];         // transaction barriers, one per parity
+};
+
+// The column loop for one CTA.  GENERAL = true is rank 0, which owns the first QR_NB rows of the panel (the diagonal
+// block: rows at or above the diagonal are masked, row j is pushed to the cluster, the T factor is accumulated);
+// GENERAL = false are the CTAs below, whose inner loops are bare multiply-adds.  A finished column c stays UNSCALED in
+// registers (v = sc_c * x below the diagonal); the factor is applied to its dot products and at the final store.
+template <int NW, int T, bool GENERAL>
+__device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
+                                           int m, int nb, int r_begin, int nloc, cplx* __restrict__ tau_out,
+                                           double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
   long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define PSTAMP(k) do { if (prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
+#define PSTAMP(k) do { if (GENERAL && prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
   const int rank = (int)cl.block_rank();
-  const int rs = (m + QR_CL - 1) / QR_CL;
-  const int r_begin = rank * rs;
-  const int nloc = max(0, min(m, r_begin + rs) - r_begin);
   const int tid = threadIdx.x, g = tid >> 5, c = tid & 31;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // staging for the coalesced load / store: a[rl*QR_LDA + c]
-  __shared__ cplx part[NW][QR_NB];               // per-warp partial dots
-  __shared__ cplx colbuf[NW][T];                 // current column on the rows of warp g (zero on rows <= j)
-  __shared__ cplx rowl[QR_NB];                   // row j of the panel (owner CTA only)
-  __shared__ cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][column]: partial dots of every CTA
-  __shared__ cplx rowv[2][QR_NB];                // [parity][column]: row j of the panel (pushed by its owner)
-  __shared__ cplx Tsm[QR_NB][QR_NB + 1];         // rank 0: compact-WY T; rows {g, g+8, g+16, g+24} belong to warp g
-  __shared__ cplx gsm[8][QR_NB];                 // V^H v_j, one private copy per warp (no CTA barrier between write and use)
-  __shared__ cplx tau_s[QR_NB];
-  __shared__ double beta_s[QR_NB];
-  __shared__ __align__(8) unsigned long long full[2];   // transaction barriers, one per parity
-
-  // global -> shared: consecutive threads along rows (coalesced), 32 columns
-  for (int e = tid; e < nloc * QR_NB; e += NW * 32) {
-    const int rl = e % nloc, cc = e / nloc;
-    a[rl * QR_LDA + cc] = cc < nb ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
-  }
-  if (rank == 0)
-    for (int e = tid; e < QR_NB * (QR_NB + 1); e += NW * 32) (&Tsm[0][0])[e] = cmake(0.0, 0.0);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   cplx x[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -91,20 +79,20 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
   }
   if (c == 0) {
 #pragma unroll
-    for (int t = 0; t < T; ++t) colbuf[g][t] = (r_begin + g + NW * t > 0) ? x[t] : cmake(0.0, 0.0);
+    for (int t = 0; t < T; ++t) S.colbuf[g][t] = (!GENERAL || g + NW * t > 0) ? x[t] : cmake(0.0, 0.0);
   }
   // remote addresses of my slots in CTA g's exchange buffers (warp g pushes to CTA g)
   const uint32_t dst_rank = (uint32_t)(g < QR_CL ? g : 0);
-  const uint32_t r_xch = mapa_u32(smem_u32(&xch[0][rank][c]), dst_rank);
-  const uint32_t r_row = mapa_u32(smem_u32(&rowv[0][c]), dst_rank);
-  const uint32_t r_bar = mapa_u32(smem_u32(&full[0]), dst_rank);
-  const uint32_t l_bar = smem_u32(&full[0]);
+  const uint32_t r_xch = mapa_u32(smem_u32(&S.xch[0][rank][c]), dst_rank);
+  const uint32_t r_row = mapa_u32(smem_u32(&S.rowv[0][c]), dst_rank);
+  const uint32_t r_bar = mapa_u32(smem_u32(&S.full[0]), dst_rank);
+  const uint32_t l_bar = smem_u32(&S.full[0]);
   cl.sync();   // every CTA's barriers are initialised before anybody stores into them
 
   cplx tau_prev = cmake(0.0, 0.0);
+  cplx sc = cmake(1.0, 0.0);                     // scale of my column once it is finished
   for (int j = 0; j < nb; ++j) {
     const int par = j & 1;
-    const int jl = j - r_begin;                  // local index of row j (owner CTA: 0 <= jl < nloc)
     if (tid == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar + 8 * par), "r"(QR_TX_BYTES) : "memory");
     // ---- phase A: t_c = sum_{r>j} conj(a[r][j]) a[r][c] over my rows
@@ -112,7 +100,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     {
       cplx acc0 = cmake(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
 #pragma unroll
-      for (int t = 0; t < T; ++t) d[t] = colbuf[g][t];
+      for (int t = 0; t < T; ++t) d[t] = S.colbuf[g][t];
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         if ((t & 3) == 0) cfma_conj(acc0, d[t], x[t]);
@@ -120,26 +108,30 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
         else if ((t & 3) == 2) cfma_conj(acc2, d[t], x[t]);
         else cfma_conj(acc3, d[t], x[t]);
       }
-      part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
+      S.part[g][c] = cadd(cadd(acc0, acc1), cadd(acc2, acc3));
+      if (GENERAL) {
 #pragma unroll
-      for (int t = 0; t < T; ++t)
-        if (g + NW * t == jl) rowl[c] = x[t];
+        for (int t = 0; t < T; ++t)
+          if (g + NW * t == j) S.rowl[c] = (c < j) ? cmul(x[t], sc) : x[t];
+      }
     }
     PSTAMP(0);
     __syncthreads();
     if (g < QR_CL) {
       // warp g sums the NW partials of column c and pushes the result (and row j, if mine) to CTA g of the cluster
-      cplx p0 = cadd(part[0][c], part[1][c]), p1 = cadd(part[2][c], part[3][c]);
-      cplx p2 = cadd(part[4][c], part[5][c]), p3 = cadd(part[6][c], part[7][c]);
+      cplx p0 = cadd(S.part[0][c], S.part[1][c]), p1 = cadd(S.part[2][c], S.part[3][c]);
+      cplx p2 = cadd(S.part[4][c], S.part[5][c]), p3 = cadd(S.part[6][c], S.part[7][c]);
       if (NW > 8) {
-        p0 = cadd(p0, cadd(part[8 % NW][c], part[9 % NW][c])); p1 = cadd(p1, cadd(part[10 % NW][c], part[11 % NW][c]));
-        p2 = cadd(p2, cadd(part[12 % NW][c], part[13 % NW][c])); p3 = cadd(p3, cadd(part[14 % NW][c], part[15 % NW][c]));
+        p0 = cadd(p0, cadd(S.part[8 % NW][c], S.part[9 % NW][c])); p1 = cadd(p1, cadd(S.part[10 % NW][c], S.part[11 % NW][c]));
+        p2 = cadd(p2, cadd(S.part[12 % NW][c], S.part[13 % NW][c])); p3 = cadd(p3, cadd(S.part[14 % NW][c], S.part[15 % NW][c]));
       }
-      st_async_c16(r_xch + par * (QR_CL * QR_NB * 16), cadd(cadd(p0, p1), cadd(p2, p3)), r_bar + 8 * par);
-      if (jl >= 0 && jl < nloc) st_async_c16(r_row + par * (QR_NB * 16), rowl[c], r_bar + 8 * par);
+      cplx tot = cadd(cadd(p0, p1), cadd(p2, p3));
+      if (c < j) tot = cmul(sc, tot);            // finished column: its rows are stored unscaled
+      st_async_c16(r_xch + par * (QR_CL * QR_NB * 16), tot, r_bar + 8 * par);
+      if (GENERAL) st_async_c16(r_row + par * (QR_NB * 16), S.rowl[c], r_bar + 8 * par);
     }
     PSTAMP(1);
-    if (rank == 0 && j > 0 && g < 8) {
+    if (GENERAL && j > 0 && g < 8) {
       // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise) in the
       // shadow of the exchange: warp g owns rows i = g + 8q; lane = (q, h) sums k = h, h+8, ... and the 8 h-lanes combine
       const int jp = j - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
@@ -148,7 +140,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int k = h + 8 * kk;
-          if (k >= i && k < jp) cfma(acc, Tsm[i][k], gsm[g][k]);
+          if (k >= i && k < jp) cfma(acc, S.Tsm[i][k], S.gsm[g][k]);
         }
       }
 #pragma unroll
@@ -157,8 +149,8 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
       }
       if (h == 0) {
-        if (i < jp) Tsm[i][jp] = cneg(cmul(tau_prev, acc));
-        else if (i == jp) Tsm[jp][jp] = tau_prev;
+        if (i < jp) S.Tsm[i][jp] = cneg(cmul(tau_prev, acc));
+        else if (i == jp) S.Tsm[jp][jp] = tau_prev;
       }
       __syncwarp();
     }
@@ -167,14 +159,14 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     PSTAMP(2);
     cplx tc, tj;
     {
-      const cplx c0 = cadd(xch[par][0][c], xch[par][1][c]), c1 = cadd(xch[par][2][c], xch[par][3][c]);
-      const cplx c2 = cadd(xch[par][4][c], xch[par][5][c]), c3 = cadd(xch[par][6][c], xch[par][7][c]);
-      const double j0 = xch[par][0][j].x + xch[par][1][j].x, j1 = xch[par][2][j].x + xch[par][3][j].x;
-      const double j2 = xch[par][4][j].x + xch[par][5][j].x, j3 = xch[par][6][j].x + xch[par][7][j].x;
+      const cplx c0 = cadd(S.xch[par][0][c], S.xch[par][1][c]), c1 = cadd(S.xch[par][2][c], S.xch[par][3][c]);
+      const cplx c2 = cadd(S.xch[par][4][c], S.xch[par][5][c]), c3 = cadd(S.xch[par][6][c], S.xch[par][7][c]);
+      const double j0 = S.xch[par][0][j].x + S.xch[par][1][j].x, j1 = S.xch[par][2][j].x + S.xch[par][3][j].x;
+      const double j2 = S.xch[par][4][j].x + S.xch[par][5][j].x, j3 = S.xch[par][6][j].x + S.xch[par][7][j].x;
       tc = cadd(cadd(c0, c1), cadd(c2, c3));
       tj = cmake((j0 + j1) + (j2 + j3), 0.0);
     }
-    const cplx alpha = rowv[par][j], rowc = rowv[par][c];
+    const cplx alpha = S.rowv[par][j], rowc = S.rowv[par][c];
     const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
     const double nrm2 = aa + tj.x;
     double beta;
@@ -195,52 +187,48 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     cplx wc = rowc;
     cfma(wc, cconj(scale), tc);
     wc = cmul(cconj(tau), wc);
-    if (rank == 0 && g < 8) {
+    if (GENERAL && g < 8) {
       // g_c = V_c^H v_j = conj(V[j][c]) + scale * conj(t_c)   (c < j)
       cplx gg = cconj(rowc);
       cfma(gg, scale, cconj(tc));
-      gsm[g][c] = c < j ? gg : cmake(0.0, 0.0);
-      if (tid == 0) { tau_s[j] = tau; beta_s[j] = beta; }
+      S.gsm[g][c] = c < j ? gg : cmake(0.0, 0.0);
+      if (tid == 0) { S.tau_s[j] = tau; S.beta_s[j] = beta; }
     }
     tau_prev = tau;
+    if (c == j) sc = scale;
     PSTAMP(3);
-    // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j) with v_r = scale * a[r][j] (r > j), v_j = 1;
-    //      column j <- v below the diagonal and beta on it.  One multiply-add per element: x <- s + d * q.
+    // ---- phase D: a[r][c] -= v_r w_c (r >= j, c > j) with v_r = scale * a[r][j] (r > j), v_j = 1:  x <- x + d * q
     {
-      const cplx q = (c == j) ? scale : (c > j ? cneg(cmul(scale, wc)) : cmake(0.0, 0.0));
-      const cplx pv = (c == j) ? cmake(beta, 0.0) : wc;
+      const cplx q = c > j ? cneg(cmul(scale, wc)) : cmake(0.0, 0.0);
       if (NW > 8) {   // 512-thread variant: 128 registers per thread, so the column is re-read instead of kept
 #pragma unroll
-        for (int t = 0; t < T; ++t) d[t] = colbuf[g][t];
+        for (int t = 0; t < T; ++t) d[t] = S.colbuf[g][t];
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const int r = r_begin + g + NW * t;
-        cplx s = (c == j && r > j) ? cmake(0.0, 0.0) : x[t];
-        cfma(s, d[t], q);
-        if (r == j && c >= j) s = (c == j) ? pv : csub(s, pv);
-        x[t] = s;
+        cfma(x[t], d[t], q);
+        if (GENERAL) {
+          const int r = g + NW * t;
+          if (r == j && c >= j) x[t] = (c == j) ? cmake(beta, 0.0) : csub(x[t], wc);
+        }
       }
       if (c == j + 1) {
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int rl = g + NW * t;
-          colbuf[g][t] = (r_begin + rl > j + 1 && rl < nloc) ? x[t] : cmake(0.0, 0.0);
-        }
+        for (int t = 0; t < T; ++t) S.colbuf[g][t] = (!GENERAL || g + NW * t > j + 1) ? x[t] : cmake(0.0, 0.0);
       }
       __syncwarp();
     }
     PSTAMP(4);
   }
-  if (prof && rank == 0 && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
-  if (rank == 0 && g < 8) {   // T column of the last reflector
+  if (GENERAL && prof && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
+  if (GENERAL && g < 8) {   // T column of the last reflector
     const int jp = nb - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
     cplx acc = cmake(0.0, 0.0);
     if (i < jp) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = h + 8 * kk;
-        if (k >= i && k < jp) cfma(acc, Tsm[i][k], gsm[g][k]);
+        if (k >= i && k < jp) cfma(acc, S.Tsm[i][k], S.gsm[g][k]);
       }
     }
 #pragma unroll
@@ -249,28 +237,63 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
       acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
     }
     if (h == 0) {
-      if (i < jp) Tsm[i][jp] = cneg(cmul(tau_prev, acc));
-      else if (i == jp) Tsm[jp][jp] = tau_prev;
+      if (i < jp) S.Tsm[i][jp] = cneg(cmul(tau_prev, acc));
+      else if (i == jp) S.Tsm[jp][jp] = tau_prev;
     }
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int rl = g + NW * t;
-    if (rl < nloc) a[rl * QR_LDA + c] = x[t];
+    if (rl < nloc) a[rl * QR_LDA + c] = (!GENERAL || rl > c) ? cmul(x[t], sc) : x[t];
   }
   __syncthreads();
   for (int e = tid; e < nloc * nb; e += NW * 32) {
     const int rl = e % nloc, cc = e / nloc;
     A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
   }
-  if (rank == 0) {
+  if (GENERAL) {
     for (int e = tid; e < QR_NB * QR_NB; e += NW * 32) {
       int i = e % QR_NB, k = e / QR_NB;
-      Tout[e] = (i < nb && k < nb) ? Tsm[i][k] : cmake(0.0, 0.0);
+      Tout[e] = (i < nb && k < nb) ? S.Tsm[i][k] : cmake(0.0, 0.0);
     }
-    if (tid < nb) { tau_out[tid] = tau_s[tid]; dabs_out[tid] = fabs(beta_s[tid]); }
+    if (tid < nb) { tau_out[tid] = S.tau_s[tid]; dabs_out[tid] = fabs(S.beta_s[tid]); }
   }
   cl.sync();  // no CTA may exit while others may still write into its shared memory
+}
+
+// Row split: rank 0 owns rows [0, QR_NB) (or all m of them if fewer), the rest is dealt evenly to ranks 1..QR_CL-1.
+__host__ __device__ __forceinline__ int panel_rows_below(int m) { return (max(0, m - QR_NB) + QR_CL - 2) / (QR_CL - 1); }
+
+template <int NW, int T>
+__global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(NW * 32)
+qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
+                double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
+  const int rs1 = panel_rows_below(m);
+  const int r_begin = rank == 0 ? 0 : min(m, QR_NB + (rank - 1) * rs1);
+  const int nloc = rank == 0 ? min(m, QR_NB) : max(0, min(m, r_begin + rs1) - r_begin);
+  const int tid = threadIdx.x;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // staging for the coalesced load / store: a[rl*QR_LDA + c]
+  __shared__ __align__(16) PanelSmem<NW> S;
+
+  // global -> shared: consecutive threads along rows (coalesced), 32 columns
+  for (int e = tid; e < nloc * QR_NB; e += NW * 32) {
+    const int rl = e % nloc, cc = e / nloc;
+    a[rl * QR_LDA + cc] = cc < nb ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
+  }
+  if (rank == 0)
+    for (int e = tid; e < QR_NB * (QR_NB + 1); e += NW * 32) (&S.Tsm[0][0])[e] = cmake(0.0, 0.0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (rank == 0) panel_body<NW, QR_NB / NW, true>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
+  else panel_body<NW, T, false>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
 }
 
 // =====================================================================================================
@@ -390,6 +413,133 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
   }
 }
 
+// Same operation for NARROW C (few column blocks): an 8-CTA cluster per 8-column block splits the rows, so that the
+// two latency-bound sweeps over V (L2 loads in fragment order) are 8x shorter; the 32 x 8 partial products V^H C are
+// exchanged through distributed shared memory.  Used for the columns of the next panel, which sit on the critical path
+// of the factorization, and for the tail of the trailing matrix where one CTA per block would leave most SMs idle.
+#define LC_CL 8
+__global__ void __cluster_dims__(LC_CL, 1, 1) __launch_bounds__(256)
+larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict__ T, int conjT,
+                     cplx* __restrict__ C, int ldc, int ncols) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* slots = reinterpret_cast<cplx*>(smem_raw);           // [LC_CL][256]: partial W of every CTA of the cluster
+  __shared__ cplx Tsm[QR_NB][QR_NB + 1];
+  __shared__ double Wp[4][4][32][4];
+  __shared__ cplx W1[QR_NB][8], W2[QR_NB][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lo = lane >> 2, lk = lane & 3;
+  const int rank = (int)cl.block_rank();
+  const int c0 = (blockIdx.x / LC_CL) * 8;
+  const int rchunk = (((m + LC_CL - 1) / LC_CL) + 7) / 8 * 8;
+  const int rbeg = min(m, rank * rchunk), rend = min(m, rbeg + rchunk);
+
+  for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) Tsm[e % QR_NB][e / QR_NB] = T[e];
+
+  // ---- phase 1: partial W = V^H C over my rows (32 x 8); 8-row steps dealt to the warps
+  double cr[4][2], ci[4][2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) cr[it][0] = cr[it][1] = ci[it][0] = ci[it][1] = 0.0;
+  const bool colok = (c0 + lo) < ncols;
+  for (int r0 = rbeg + 8 * warp; r0 < rend; r0 += 64) {
+    cplx av[2][4], bv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + 4 * u + lk;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int c = it * 8 + lo;
+        av[u][it] = (r >= QR_NB && r < rend) ? V[(size_t)c * ldv + r] : (r < rend ? vmask_load(V, ldv, m, r, c) : cmake(0.0, 0.0));
+      }
+      bv[u] = (r < rend && colok) ? C[(size_t)(c0 + lo) * ldc + r] : cmake(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {   // A operand = conj(V)
+        dmma884(cr[it][0], cr[it][1], av[u][it].x, bv[u].x);
+        dmma884(cr[it][0], cr[it][1], av[u][it].y, bv[u].y);
+        dmma884(ci[it][0], ci[it][1], av[u][it].x, bv[u].y);
+        dmma884(ci[it][0], ci[it][1], -av[u][it].y, bv[u].x);
+      }
+  }
+  if (warp >= 4) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      Wp[warp - 4][it][lane][0] = cr[it][0]; Wp[warp - 4][it][lane][1] = cr[it][1];
+      Wp[warp - 4][it][lane][2] = ci[it][0]; Wp[warp - 4][it][lane][3] = ci[it][1];
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      Wp[warp][it][lane][0] += cr[it][0]; Wp[warp][it][lane][1] += cr[it][1];
+      Wp[warp][it][lane][2] += ci[it][0]; Wp[warp][it][lane][3] += ci[it][1];
+    }
+  }
+  __syncthreads();
+  {
+    const int i = tid >> 3, c = tid & 7;            // element W[i][c] of my partial goes to slot `rank` of every CTA
+    const int it = i >> 3, ln = (i & 7) * 4 + (c >> 1), e = c & 1;
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { sr += Wp[w][it][ln][e]; si += Wp[w][it][ln][2 + e]; }
+    const cplx v = cmake(sr, si);
+#pragma unroll
+    for (int dst = 0; dst < LC_CL; ++dst) {
+      cplx* rs = cl.map_shared_rank(slots, dst);
+      rs[rank * 256 + tid] = v;
+    }
+  }
+  cl.sync();
+  {
+    cplx s0 = cadd(slots[tid], slots[256 + tid]), s1 = cadd(slots[2 * 256 + tid], slots[3 * 256 + tid]);
+    cplx s2 = cadd(slots[4 * 256 + tid], slots[5 * 256 + tid]), s3 = cadd(slots[6 * 256 + tid], slots[7 * 256 + tid]);
+    W1[tid >> 3][tid & 7] = cadd(cadd(s0, s1), cadd(s2, s3));
+  }
+  __syncthreads();
+  // ---- phase 2: W <- op(T) W
+  {
+    const int i = tid >> 3, c = tid & 7;
+    cplx acc = cmake(0.0, 0.0);
+    if (conjT) { for (int k = 0; k < QR_NB; ++k) cfma_conj(acc, Tsm[k][i], W1[k][c]); }
+    else       { for (int k = 0; k < QR_NB; ++k) cfma(acc, Tsm[i][k], W1[k][c]); }
+    W2[i][c] = acc;
+  }
+  __syncthreads();
+  // ---- phase 3: C -= V W on my rows (K = 32)
+  for (int r0 = rbeg + 8 * warp; r0 < rend; r0 += 64) {
+    const int r = r0 + lo;
+    cplx av[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int c = kk * 4 + lk;
+      av[kk] = (r0 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c);
+    }
+    double dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const cplx b = W2[kk * 4 + lk][lo];
+      dmma884(dr[0], dr[1], av[kk].x, b.x);
+      dmma884(dr[0], dr[1], -av[kk].y, b.y);
+      dmma884(di[0], di[1], av[kk].x, b.y);
+      dmma884(di[0], di[1], av[kk].y, b.x);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = c0 + 2 * lk + e;
+      if (r < rend && col < ncols) {
+        cplx* p = C + (size_t)col * ldc + r;
+        cplx t = *p;
+        t.x -= dr[e]; t.y -= di[e];
+        *p = t;
+      }
+    }
+  }
+  cl.sync();   // nobody exits while its shared memory may still be written... (all remote stores precede the first sync)
+}
+
 __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
   size_t tot = (size_t)n * n;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
@@ -410,24 +560,39 @@ static int launch_panel_t(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx
   return 0;
 }
 static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* T) {
-  const int rs = (m + QR_CL - 1) / QR_CL;
-  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * rs + 8);
+  const int rs = panel_rows_below(m);   // rows per CTA below the diagonal block
+  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * max(rs, QR_NB) + 8);
   if (rs <= 8) return launch_panel_t<8, 1>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 16) return launch_panel_t<8, 2>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 32) return launch_panel_t<8, 4>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 64) return launch_panel_t<8, 8>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 96) return launch_panel_t<8, 12>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 128) return launch_panel_t<8, 16>(st, A, lda, m, nb, tau, dabs, T, smem);
-  if (rs <= 160) return launch_panel_t<16, 10>(st, A, lda, m, nb, tau, dabs, T, smem);
-  if (rs <= 208) return launch_panel_t<16, 13>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 144) return launch_panel_t<8, 18>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 192) return launch_panel_t<16, 12>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 224) return launch_panel_t<16, 14>(st, A, lda, m, nb, tau, dabs, T, smem);
   if (rs <= 256) return launch_panel_t<16, 16>(st, A, lda, m, nb, tau, dabs, T, smem);
+  if (rs <= 320) return launch_panel_t<16, 20>(st, A, lda, m, nb, tau, dabs, T, smem);
   snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m);
   return -1;
 }
 
+int g_larfb_cluster_max_cols = 256;   // column count up to which the row-split cluster kernel is used
 static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cplx* T, int conjT, cplx* C, int ldc,
                         int ncols) {
   if (ncols <= 0) return 0;
+  if (ncols <= g_larfb_cluster_max_cols && m >= 64) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(cplx) * LC_CL * 256;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(larfb_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    larfb_cluster_kernel<<<((ncols + 7) / 8) * LC_CL, 256, smem, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return 0;
+  }
   larfb_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
