@@ -40,6 +40,12 @@ __device__ __forceinline__ void st_pub(cplx* p, cplx v) {
 __device__ __forceinline__ void st_sent(cplx* p) {
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(LU_SENT) : "memory");
 }
+// L2 load issued in program order relative to the other volatile asm statements (no memory clobber: ordinary accesses may move)
+__device__ __forceinline__ cplx ld_cg_issue(const cplx* p) {
+  cplx v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ cplx ldcg2(const cplx* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
 // 4x4 complex e^{-power*dtau*V(op)} (interactions.jl:102-141), element (r,c):  [C S 0 R; cS C -R 0; 0 -R C cS; R 0 S C]
@@ -292,17 +298,21 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       }
     } else {
       const int tp = tid - 128;
-      // ---- loads: everything is issued before anything is waited for
+      // ---- loads: everything is issued before anything is waited for (volatile asm keeps the issue order; the values
+      // go to shared memory only after the A/B loads below are in flight)
       // (G) plain L2 loads: 4x4 block of site i+1, the two cross blocks between sites i+1 and i, my rows/cols of G
+      cplx gq = cmake(0.0, 0.0), gcv = gq, grv = gq;
       if (have_next) {
         const int site = i + 1;
-        if (tp < 16) g4r[tp] = ldcg2(a.G + (size_t)(site + (tp >> 2) * N) * n + site + (tp & 3) * N);            // [r + 4c]
-        else if (tp < 32) { const int q = tp - 16; Gx1[q] = ldcg2(a.G + (size_t)(i + (q & 3) * N) * n + site + (q >> 2) * N); }   // [r*4+k] = G[i+1+rN, i+kN]
-        else if (tp < 48) { const int q = tp - 32; Gx2[q] = ldcg2(a.G + (size_t)(site + (q & 3) * N) * n + i + (q >> 2) * N); }   // [k*4+c] = G[i+kN, i+1+cN]
-        for (int e = tp; e < nown * 4; e += 128) {
-          const int rl = e >> 2, k = e & 3;
-          gcol[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(site + k * N) * n + row0 + rl);
-          grow[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(row0 + rl) * n + site + k * N);
+        const cplx* pq = nullptr;
+        if (tp < 16) pq = a.G + (size_t)(site + (tp >> 2) * N) * n + site + (tp & 3) * N;                                   // [r + 4c]
+        else if (tp < 32) { const int q = tp - 16; pq = a.G + (size_t)(i + (q & 3) * N) * n + site + (q >> 2) * N; }        // [r*4+k] = G[i+1+rN, i+kN]
+        else if (tp < 48) { const int q = tp - 32; pq = a.G + (size_t)(site + (q & 3) * N) * n + i + (q >> 2) * N; }        // [k*4+c] = G[i+kN, i+1+cN]
+        if (pq) gq = ld_cg_issue(pq);
+        if (tp < nown * 4) {
+          const int rl = tp >> 2, k = tp & 3;
+          gcv = ld_cg_issue(a.G + (size_t)(site + k * N) * n + row0 + rl);
+          grv = ld_cg_issue(a.G + (size_t)(row0 + rl) * n + site + k * N);
         }
       }
       // (A/B) all np pending columns for the rows/cols of site i+1, published by their owner CTAs (spin on the NaN
@@ -317,6 +327,15 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         for (int u = 0; u < 8; ++u)
           if (have_next && p8 + 16 * u < np)
             asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
+        if (have_next) {   // G values: into shared memory while the A/B loads are in flight
+          if (tp < 16) g4r[tp] = gq; else if (tp < 32) Gx1[tp - 16] = gq; else if (tp < 48) Gx2[tp - 32] = gq;
+          if (tp < nown * 4) { gcol[nb * rpc * 4 + tp] = gcv; grow[nb * rpc * 4 + tp] = grv; }
+          for (int e = tp + 128; e < nown * 4; e += 128) {
+            const int rl = e >> 2, k = e & 3;
+            gcol[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(i + 1 + k * N) * n + row0 + rl);
+            grow[nb * rpc * 4 + e] = ldcg2(a.G + (size_t)(row0 + rl) * n + i + 1 + k * N);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (have_next && p8 + 16 * u < np) {
