@@ -1023,7 +1023,7 @@ extern "C" int dqmc_lu_profile(dqmc_ctx* c, int32_t enable, int64_t* out16) {
   CU(c, cudaSetDevice(c->p.device));
   c->lu_prof = enable != 0;
   if (out16) {
-    CU(c, cudaMemcpyAsync(out16, c->d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(out16, c->d_prof, sizeof(long long) * 24, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
   }
   return 0;

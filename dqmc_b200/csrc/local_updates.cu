@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   // optional cycle profile of CTA 0: arrival stamps before the two CTA barriers of an iteration (a clock read right
   // after bar.sync would capture the barrier's issue, not its release)
   const bool prof = (a.prof != nullptr) && blockIdx.x == 0;
-  __shared__ long long stampA[8], stampB[8];
-  __shared__ long long p_role[8];
-  if (tid < 8) p_role[tid] = 0;
+  __shared__ long long stampA[8], stampB[8], stampP[8];
+  __shared__ long long p_role[8], p_role1[8];
+  if (tid < 8) { p_role[tid] = 0; p_role1[tid] = 0; }
   long long p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
   __syncthreads();
   const long long t_begin = clock64();
@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         }
       }
     }
+    if (prof && lane == 0) stampP[warp] = clock64();
     if (warp < 4) {
       // speculative part of a possible accept (does not depend on the decision): G_eff[r, i+kN] - delta for my rows and
       // G_eff[i+kN, c] for my columns, 2 threads per dot product over the pending columns
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     __syncthreads();
     if (prof && tid == 0) {
       long long relA = stampA[0], relB = stampB[0];
-      for (int w = 0; w < 8; ++w) { relA = max(relA, stampA[w]); relB = max(relB, stampB[w]); p_role[w] += stampA[w] - rel_prev; }
+      for (int w = 0; w < 8; ++w) { relA = max(relA, stampA[w]); relB = max(relB, stampB[w]); p_role[w] += stampA[w] - rel_prev; p_role1[w] += stampP[w] - rel_prev; }
       p_s1 += relA - rel_prev;
       if (do_flush) p_flush += relB - relA; else if (accepted) p_rest_acc += relB - relA; else p_rest_rej += relB - relA;
       rel_prev = relB;
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     // [4] #flushes, [5] accepts, [6] stage 2 of rejected sites, [8+w] stage-1 role time of warp w
     a.prof[0] = clock64() - t_begin; a.prof[1] = p_s1; a.prof[2] = p_rest_acc; a.prof[3] = p_flush; a.prof[4] = n_fl;
     a.prof[5] = nacc; a.prof[6] = p_rest_rej;
-    for (int w = 0; w < 8; ++w) a.prof[8 + w] = p_role[w];
+    for (int w = 0; w < 8; ++w) { a.prof[8 + w] = p_role[w]; a.prof[16 + w] = p_role1[w]; }
   }
 
   if (blockIdx.x == 0 && tid == 0) {

@@ -20,3 +20,4 @@ print(f" cycles total {tot}  stage1 {p[1]} ({p[1]/tot:.0%})  stage2(acc) {p[2]} 
 print(" per-site stage1 %.0f cyc; per-accept stage2 %.0f cyc; per-reject tail %.0f; per-flush-iteration %.0f cyc" % (p[1]/N, p[2]/max(p[5]-p[4],1), p[6]/max(N-p[5],1), p[3]/max(p[4],1)))
 print(" role cycles/site: decision %.0f  prep %s  prefetch %s" % (p[8]/N, [int(p[9+k]/N) for k in range(3)], [int(p[12+k]/N) for k in range(4)]))
 mc.close()
+print(" role-only cycles/site (before the speculative dot products): %s" % [int(p[16+k]/N) for k in range(8)])
