@@ -19,7 +19,7 @@
 char g_errbuf[512] = {0};
 long long g_launches = 0;
 
-enum { F_HBH = 0, F_HA, F_HBH_MU, F_HBHINV, F_HAINV, F_MUINV_HBHINV, F_COUNT };
+enum { F_HBH = 0, F_HA, F_HBH_MU, F_HBHINV, F_HAINV, F_MUINV_HBHINV, F_HAH, F_HAHINV, F_COUNT };
 enum { TM_WRAP = 0, TM_LOCAL, TM_UDT, TM_GREENS, TM_SWEEP, TM_COUNT };
 
 struct HostCSC {
@@ -69,6 +69,11 @@ struct dqmc_ctx {
   bool lu_prof;
   double* d_logdet;
   double* d_check;     // [0] running max, [1] scratch
+  // time-displaced Green's functions (fermion_measurements.jl:1343-1541), allocated on first use
+  cplx *Gt0, *G0t;                 // [M][n*n]
+  cplx *td_u[4], *td_t[4];         // UDT chains BT0Inv, BBetaT, BT0, BBetaTInv: [K][n*n]
+  double* td_d[4];                 // [K][n]
+  cplx* td_eye; double* td_ones;
   bool have_nbr, ops_ready;
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
@@ -199,6 +204,8 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
   TRY(c, dmalloc(c, &c->d_prof, 32)); c->lu_prof = false;
   TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
+  c->Gt0 = c->G0t = nullptr; c->td_eye = nullptr; c->td_ones = nullptr;
+  for (int i = 0; i < 4; ++i) { c->td_u[i] = c->td_t[i] = nullptr; c->td_d[i] = nullptr; }
   c->gb_G = c->gb_u_stack = c->gb_t_stack = nullptr; c->gb_d_stack = c->gb_hs = nullptr; c->gb_log_det = 0.0;
   TRY(c, dmalloc(c, &c->d_action, 1 + 1024));
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
@@ -218,7 +225,8 @@ extern "C" int dqmc_destroy(dqmc_ctx* c) {
                   c->W[0], c->W[1], c->W[2], c->W[3], c->W[4], c->tau, c->tfac, c->trsm_work, c->dabs, c->drp_inv,
                   c->colnorm, c->perm, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
                   c->d_flags, c->d_bar, c->d_logdet, c->d_check, c->gb_G, c->gb_u_stack, c->gb_t_stack, c->gb_d_stack,
-                  c->gb_hs, c->d_action};
+                  c->gb_hs, c->d_action, c->d_prof, c->Gt0, c->G0t, c->td_eye, c->td_ones, c->td_u[0], c->td_u[1], c->td_u[2],
+                  c->td_u[3], c->td_t[0], c->td_t[1], c->td_t[2], c->td_t[3], c->td_d[0], c->td_d[1], c->td_d[2], c->td_d[3]};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < F_COUNT; ++i) { if (c->fop[i].idx) cudaFree(c->fop[i].idx); if (c->fop[i].val) cudaFree(c->fop[i].val); }
   cudaStreamDestroy(c->st);
@@ -323,7 +331,7 @@ static int csc_diag(dqmc_ctx* c, const HostCSC& m, std::vector<cplx>* d) {
 }
 
 static int finalize_operators(dqmc_ctx* c) {
-  for (int i = 0; i < DQMC_OP_COUNT; ++i) if (!c->csc[i].set) return 0;   // wait until all six are there
+  for (int i = 0; i <= DQMC_OP_MU_INV; ++i) if (!c->csc[i].set) return 0;   // wait until the six factors of B are there
   HostQuad hbh, ha, hbhinv, hainv;
   TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_B], &hbh));
   TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_A], &ha));
@@ -348,6 +356,14 @@ static int finalize_operators(dqmc_ctx* c) {
   TRY(c, upload_quad(c, hbhinv, &c->fop[F_HBHINV]));
   TRY(c, upload_quad(c, hainv, &c->fop[F_HAINV]));
   TRY(c, upload_quad(c, muinv_hbhinv, &c->fop[F_MUINV_HBHINV]));
+  // optional: the half-step factors of group A, used only by effective_greens2greens! (fermion_measurements.jl:1125-1142)
+  if (c->csc[DQMC_OP_HOP_HALF_A].set && c->csc[DQMC_OP_HOP_HALF_INV_A].set) {
+    HostQuad hah, hahinv;
+    TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_A], &hah));
+    TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_INV_A], &hahinv));
+    TRY(c, upload_quad(c, hah, &c->fop[F_HAH]));
+    TRY(c, upload_quad(c, hahinv, &c->fop[F_HAHINV]));
+  }
   c->ops_ready = true;
   return 0;
 }
@@ -1039,6 +1055,197 @@ extern "C" int dqmc_checks(dqmc_ctx* c, double* max_propagation_error, int64_t* 
   CU(c, cudaStreamSynchronize(c->st));
   if (max_propagation_error) *max_propagation_error = chk[0];
   if (nonreal) *nonreal = flags[1];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- time-displaced G
+// [Ua Da Ta + Ub Db Tb]^-1 (inv_sum_udts_scalettar!, linalg.jl:512-567), all operands on the device, into `res`.
+// Same scale separation as the reference (Dp = max(D,1), Dm = min(D,1)):
+//   res = Tb^-1 Dbp^-1 [ Dam (Ta Tb^-1) Dbp^-1 + Dap^-1 (Ua^H Ub) Dbm ]^-1 Dap^-1 Ua^H
+// with every inverse applied through a Householder QR (Q^H folded into the right-hand side) and a triangular solve,
+// as in calculate_greens_dev; the reference's two intermediate pivoted UDTs + LU solves are replaced by that.
+static int inv_sum_udts_dev(dqmc_ctx* c, const cplx* Ua, const double* Da, const cplx* Ta, const cplx* Ub, const double* Db,
+                            const cplx* Tb, cplx* res) {
+  const int n = c->n;
+  const size_t nn = (size_t)n * n;
+  const EwTerm none = {nullptr, 0, nullptr, 0, nullptr, 0};
+  const QrAsync* la = c->lookahead ? &c->qra : nullptr;
+  // (Ta Tb^-1)^H = (Tb^H)^-1 Ta^H
+  TRY(c, ew_combine(c->st, n, EwTerm{Tb, 1, nullptr, 0, nullptr, 0}, none, 1.0, c->W[0], c->num_sms));
+  TRY(c, ew_combine(c->st, n, EwTerm{Ta, 1, nullptr, 0, nullptr, 0}, none, 1.0, c->W[1], c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[0], n, n, c->tau, c->dabs, c->tfac, c->W[1], n, n, c->num_sms, la));
+  TRY(c, trsm_upper(c->st, c->W[0], n, n, c->W[1], n, n, c->trsm_work, nullptr, c->num_sms));
+  TRY(c, zgemm(c->st, OP_C, OP_N, n, n, n, ONE, Ua, n, Ub, n, ZERO, c->W[2], n, c->num_sms));
+  TRY(c, ew_combine(c->st, n, EwTerm{c->W[1], 1, Da, 3, Db, 2}, EwTerm{c->W[2], 0, Da, 2, Db, 3}, 1.0, c->W[0], c->num_sms));
+  // res <- Dbp^-1 [mat]^-1 Dap^-1 Ua^H
+  TRY(c, ew_combine(c->st, n, EwTerm{Ua, 1, Da, 2, nullptr, 0}, none, 1.0, res, c->num_sms));
+  TRY(c, qr_factor(c->st, c->W[0], n, n, c->tau, c->dabs, c->tfac, res, n, n, c->num_sms, la));
+  TRY(c, trsm_upper(c->st, c->W[0], n, n, res, n, n, c->trsm_work, nullptr, c->num_sms));
+  TRY(c, ew_combine(c->st, n, EwTerm{res, 0, Db, 2, nullptr, 0}, none, 1.0, res, c->num_sms));
+  // res <- Tb^-1 res
+  CU(c, cudaMemcpyAsync(c->W[0], Tb, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+  TRY(c, qr_factor(c->st, c->W[0], n, n, c->tau, c->dabs, c->tfac, res, n, n, c->num_sms, la));
+  TRY(c, trsm_upper(c->st, c->W[0], n, n, res, n, n, c->trsm_work, nullptr, c->num_sms));
+  return 0;
+}
+
+// effective_greens2greens! (fermion_measurements.jl:1125-1142): G <- hA½^-1 hB½^-1 G hB½ hA½
+static int effective_greens2greens_dev(dqmc_ctx* c, cplx* g) {
+  if (!c->fop[F_HAH].idx || !c->fop[F_HAHINV].idx)
+    CTX_FAIL(c, "effective_greens2greens: operators DQMC_OP_HOP_HALF_A / DQMC_OP_HOP_HALF_INV_A not set");
+  Chain r; r.nsteps = 0;
+  push_op(r, c->fop[F_HBH], OP_T); push_op(r, c->fop[F_HAH], OP_T);
+  TRY(c, run_chain(c, true, g, r, nullptr, nullptr));
+  Chain l; l.nsteps = 0;
+  push_op(l, c->fop[F_HBHINV], OP_N); push_op(l, c->fop[F_HAHINV], OP_N);
+  TRY(c, run_chain(c, false, g, l, nullptr, nullptr));
+  return 0;
+}
+
+static int allocate_tdgfs(dqmc_ctx* c) {
+  if (c->Gt0) return 0;
+  const size_t n = c->n, nn = n * n, K = c->M / c->sm;
+  CU(c, cudaMalloc((void**)&c->Gt0, sizeof(cplx) * nn * c->M));
+  CU(c, cudaMalloc((void**)&c->G0t, sizeof(cplx) * nn * c->M));
+  for (int s = 0; s < 4; ++s) {
+    CU(c, cudaMalloc((void**)&c->td_u[s], sizeof(cplx) * nn * K));
+    CU(c, cudaMalloc((void**)&c->td_t[s], sizeof(cplx) * nn * K));
+    CU(c, cudaMalloc((void**)&c->td_d[s], sizeof(double) * n * K));
+  }
+  CU(c, cudaMalloc((void**)&c->td_eye, sizeof(cplx) * nn));
+  CU(c, cudaMalloc((void**)&c->td_ones, sizeof(double) * n));
+  TRY(c, set_identity(c->st, c->td_eye, (int)n, (int)n, c->num_sms));
+  TRY(c, fill_ones(c->st, c->td_ones, (int)n));
+  return 0;
+}
+
+// calc_Bchain_udts! (fermion_measurements.jl:1434-1503) into stack s; entries stored in the reference's final order
+// (already reversed for dir = RIGHT).
+static int calc_Bchain_udts_dev(dqmc_ctx* c, int s, bool invert, bool left) {
+  const int n = c->n, K = c->M / c->sm;
+  const size_t nn = (size_t)n * n;
+  const bool rightmult = (!left && !invert) || (left && invert);
+  const int op = !invert ? (left ? DQMC_B_LEFT : DQMC_B_RIGHT) : (left ? DQMC_B_INV_RIGHT : DQMC_B_INV_LEFT);
+  for (int i = 0; i < K; ++i) {
+    const int ridx = left ? i : K - 1 - i;                   // index into s.ranges
+    const int at = ridx, prev = left ? ridx - 1 : ridx + 1;  // storage positions of this and the previous element
+    cplx* U = c->td_u[s] + (size_t)at * nn; cplx* T = c->td_t[s] + (size_t)at * nn; double* D = c->td_d[s] + (size_t)at * n;
+    const cplx* src = i == 0 ? c->td_eye : (rightmult ? c->td_t[s] + (size_t)prev * nn : c->td_u[s] + (size_t)prev * nn);
+    const double* dprev = i == 0 ? nullptr : c->td_d[s] + (size_t)prev * n;
+    CU(c, cudaMemcpyAsync(c->W[0], src, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    const int lo = 1 + ridx * c->sm, hi = (ridx + 1) * c->sm;
+    Chain ch; ch.nsteps = 0;
+    for (int k = 0; k < c->sm; ++k) {
+      const int slice = left ? lo + k : hi - k;
+      const bool last = (k == c->sm - 1);
+      push_B(c, ch, op, slice);
+      if (last || ch.nsteps + 4 > DQMC_MAX_CHAIN) {
+        TRY(c, run_chain(c, rightmult, c->W[0], ch, (last && !rightmult) ? dprev : nullptr, (last && !rightmult) ? c->colnorm : nullptr));
+        ch.nsteps = 0;
+      }
+    }
+    if (rightmult) {
+      if (dprev) TRY(c, ew_combine(c->st, n, EwTerm{c->W[0], 0, dprev, 1, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, 1.0, c->W[0], c->num_sms));
+      TRY(c, colnorm2(c->st, c->W[0], n, n, c->colnorm));
+      TRY(c, udt_dev(c, c->W[3], D));
+      CU(c, cudaMemcpyAsync(T, c->W[2], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+      if (i == 0) CU(c, cudaMemcpyAsync(U, c->W[3], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+      else TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->td_u[s] + (size_t)prev * nn, n, c->W[3], n, ZERO, U, n, c->num_sms));
+    } else {
+      TRY(c, udt_dev(c, U, D));
+      if (i == 0) CU(c, cudaMemcpyAsync(T, c->W[2], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+      else TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[2], n, c->td_t[s] + (size_t)prev * nn, n, ZERO, T, n, c->num_sms));
+    }
+  }
+  return 0;
+}
+
+// measure_tdgfs! (fermion_measurements.jl:1343-1407) + fill_tdgf! (:1509-1541)
+extern "C" int dqmc_measure_tdgfs(dqmc_ctx* c) {
+  CU(c, cudaSetDevice(c->p.device));
+  NEED_OPS(c);
+  TRY(c, allocate_tdgfs(c));
+  const int n = c->n, M = c->M, sm = c->sm, K = M / sm;
+  const size_t nn = (size_t)n * n;
+  TRY(c, calc_Bchain_udts_dev(c, 0, true, true));     // BT0Inv
+  TRY(c, calc_Bchain_udts_dev(c, 1, false, false));   // BBetaT
+  TRY(c, calc_Bchain_udts_dev(c, 2, false, true));    // BT0
+  TRY(c, calc_Bchain_udts_dev(c, 3, true, false));    // BBetaTInv
+  auto U = [&](int s, int i) { return c->td_u[s] + (size_t)i * nn; };
+  auto T = [&](int s, int i) { return c->td_t[s] + (size_t)i * nn; };
+  auto D = [&](int s, int i) { return c->td_d[s] + (size_t)i * n; };
+  for (int i = 0; i < K; ++i) {
+    cplx* gt0 = c->Gt0 + (size_t)(i * sm) * nn;
+    cplx* g0t = c->G0t + (size_t)(i * sm) * nn;
+    if (i > 0) {
+      TRY(c, inv_sum_udts_dev(c, U(0, i - 1), D(0, i - 1), T(0, i - 1), U(1, i), D(1, i), T(1, i), gt0));
+      TRY(c, inv_sum_udts_dev(c, U(2, i - 1), D(2, i - 1), T(2, i - 1), U(3, i), D(3, i), T(3, i), g0t));
+    } else {   // inv_one_plus_udt_scalettar! = the same sum with (1, 1, 1) as first operand
+      TRY(c, inv_sum_udts_dev(c, c->td_eye, c->td_ones, c->td_eye, U(1, 0), D(1, 0), T(1, 0), gt0));
+      TRY(c, inv_sum_udts_dev(c, c->td_eye, c->td_ones, c->td_eye, U(3, 0), D(3, 0), T(3, 0), g0t));
+    }
+    TRY(c, effective_greens2greens_dev(c, gt0));
+    TRY(c, effective_greens2greens_dev(c, g0t));
+  }
+  // fill_tdgf!: 0-based tau; reference Mhalf = M/2 + 1
+  const int mhalf = M / 2;
+  for (int tau = mhalf; tau < M; ++tau) {
+    if (tau % sm == 0) continue;
+    CU(c, cudaMemcpyAsync(c->Gt0 + (size_t)tau * nn, c->Gt0 + (size_t)(tau - 1) * nn, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    TRY(c, apply_B(c, DQMC_B_LEFT, tau + 1, c->Gt0 + (size_t)tau * nn));
+    CU(c, cudaMemcpyAsync(c->G0t + (size_t)tau * nn, c->G0t + (size_t)(tau - 1) * nn, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    TRY(c, apply_B(c, DQMC_B_INV_RIGHT, tau + 1, c->G0t + (size_t)tau * nn));
+  }
+  for (int tau = mhalf - 1; tau >= 0; --tau) {
+    if (tau % sm == 0) continue;
+    CU(c, cudaMemcpyAsync(c->Gt0 + (size_t)tau * nn, c->Gt0 + (size_t)(tau + 1) * nn, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    TRY(c, apply_B(c, DQMC_B_INV_LEFT, tau + 2, c->Gt0 + (size_t)tau * nn));
+    CU(c, cudaMemcpyAsync(c->G0t + (size_t)tau * nn, c->G0t + (size_t)(tau + 1) * nn, sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+    TRY(c, apply_B(c, DQMC_B_RIGHT, tau + 2, c->G0t + (size_t)tau * nn));
+  }
+  for (int tau = 0; tau < M; ++tau)   // minus sign of G(0,tau) (:1402-1404)
+    TRY(c, ew_combine(c->st, n, EwTerm{c->G0t + (size_t)tau * nn, 0, nullptr, 0, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, -1.0,
+                      c->G0t + (size_t)tau * nn, c->num_sms));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_get_tdgf(dqmc_ctx* c, int which, int32_t slice, double* out) {
+  CU(c, cudaSetDevice(c->p.device));
+  if (!c->Gt0) CTX_FAIL(c, "dqmc_get_tdgf: call dqmc_measure_tdgfs first");
+  if (slice < 1 || slice > c->M || (which != 0 && which != 1)) CTX_FAIL(c, "dqmc_get_tdgf: bad argument");
+  const size_t nn = (size_t)c->n * c->n;
+  CU(c, cudaMemcpyAsync(out, (which == 0 ? c->Gt0 : c->G0t) + (size_t)(slice - 1) * nn, sizeof(cplx) * nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int dqmc_free_tdgfs(dqmc_ctx* c) {
+  CU(c, cudaSetDevice(c->p.device));
+  CU(c, cudaStreamSynchronize(c->st));
+  void* ptrs[] = {c->Gt0, c->G0t, c->td_eye, c->td_ones, c->td_u[0], c->td_u[1], c->td_u[2], c->td_u[3], c->td_t[0], c->td_t[1],
+                  c->td_t[2], c->td_t[3], c->td_d[0], c->td_d[1], c->td_d[2], c->td_d[3]};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  c->Gt0 = c->G0t = nullptr; c->td_eye = nullptr; c->td_ones = nullptr;
+  for (int i = 0; i < 4; ++i) { c->td_u[i] = c->td_t[i] = nullptr; c->td_d[i] = nullptr; }
+  return 0;
+}
+
+// [Ua Da Ta + Ub Db Tb]^-1 of host operands (test hook for inv_sum_udts_scalettar!, linalg.jl:512-567)
+extern "C" int dqmc_inv_sum_udts(dqmc_ctx* c, const double* Ua, const double* Da, const double* Ta, const double* Ub, const double* Db,
+                                 const double* Tb, double* res) {
+  CU(c, cudaSetDevice(c->p.device));
+  const size_t n = c->n, nn = n * n;
+  // Ul, Tl, Ur, Tr, Dl, Dr are overwritten by the next stabilization anyway; borrow them as operand buffers
+  CU(c, cudaMemcpyAsync(c->Ul, Ua, sizeof(cplx) * nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Tl, Ta, sizeof(cplx) * nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Ur, Ub, sizeof(cplx) * nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Tr, Tb, sizeof(cplx) * nn, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Dl, Da, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->Dr, Db, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+  TRY(c, inv_sum_udts_dev(c, c->Ul, c->Dl, c->Tl, c->Ur, c->Dr, c->Tr, c->W[4]));
+  CU(c, cudaMemcpyAsync(res, c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
   return 0;
 }
 

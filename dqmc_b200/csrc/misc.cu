@@ -198,3 +198,58 @@ int fill_ones(cudaStream_t st, double* d, int n) {
   g_launches++;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// out = alpha * ( f_a .* op_a(A) + f_b .* op_b(B) ),   f[i][j] = rowfac(i) * colfac(j) with factors derived from a
+// real vector D by mode: 0 -> 1, 1 -> D, 2 -> 1/max(D,1), 3 -> min(D,1).  op = identity or conjugate transpose
+// (staged through a shared-memory tile so both sides stay coalesced).  In place (out == A) is allowed when
+// A is not transposed.  Used by the time-displaced Green's function path (linalg.jl:512-567).
+__device__ __forceinline__ double ew_fac(const double* D, int mode, int i) {
+  if (mode == 0 || D == nullptr) return 1.0;
+  const double d = D[i];
+  return mode == 1 ? d : (mode == 2 ? 1.0 / fmax(d, 1.0) : fmin(d, 1.0));
+}
+__global__ void __launch_bounds__(256) ew_combine_kernel(int n, EwTerm a, EwTerm b, double alpha, cplx* __restrict__ out) {
+  __shared__ cplx tile[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ntile = (n + 31) / 32;
+  for (int t = blockIdx.x; t < ntile * ntile; t += gridDim.x) {
+    const int bi = t % ntile, bj = t / ntile;      // output rows bi*32.., cols bj*32..
+    const EwTerm* terms[2] = {&a, &b};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const EwTerm& tm = *terms[k];
+      if (tm.M != nullptr && tm.trans) {
+        for (int cc = ty; cc < 32; cc += 8) {
+          const int r = bj * 32 + tx, c = bi * 32 + cc;   // element M[r, c] feeds out[c, r]
+          tile[k][cc][tx] = (r < n && c < n) ? tm.M[(size_t)c * n + r] : cmake(0.0, 0.0);
+        }
+      }
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 32; cc += 8) {
+      const int r = bi * 32 + tx, c = bj * 32 + cc;
+      if (r < n && c < n) {
+        double accx = 0.0, accy = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const EwTerm& tm = *terms[k];
+          if (tm.M == nullptr) continue;
+          cplx v;
+          if (tm.trans) { v = tile[k][tx][cc]; v.y = -v.y; }
+          else v = tm.M[(size_t)c * n + r];
+          const double f = ew_fac(tm.rd, tm.rmode, r) * ew_fac(tm.cd, tm.cmode, c);
+          accx += v.x * f; accy += v.y * f;
+        }
+        out[(size_t)c * n + r] = cmake(alpha * accx, alpha * accy);
+      }
+    }
+    __syncthreads();
+  }
+}
+int ew_combine(cudaStream_t st, int n, EwTerm a, EwTerm b, double alpha, cplx* out, int num_sms) {
+  ew_combine_kernel<<<num_sms * 4, 256, 0, st>>>(n, a, b, alpha, out);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}

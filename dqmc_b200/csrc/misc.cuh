@@ -16,3 +16,13 @@ int max_abs_diff(cudaStream_t st, const cplx* A, const cplx* B, size_t count, do
 int logdet_from_factors(cudaStream_t st, int n, const double* Dl, const double* Dr, const double* dabs, double* out);
 int set_identity(cudaStream_t st, cplx* Q, int ldq, int n, int num_sms);
 int fill_ones(cudaStream_t st, double* d, int n);
+// out = alpha * (f_a .* op_a(A) + f_b .* op_b(B)): see misc.cu (time-displaced Green's functions)
+struct EwTerm {
+  const cplx* M;       // nullptr: term absent
+  int trans;           // 0: as is, 1: conjugate transpose
+  const double* rd;    // row factor source (or nullptr)
+  int rmode;           // 0: 1, 1: D, 2: 1/max(D,1), 3: min(D,1)
+  const double* cd;    // column factor source
+  int cmode;
+};
+int ew_combine(cudaStream_t st, int n, EwTerm a, EwTerm b, double alpha, cplx* out, int num_sms);

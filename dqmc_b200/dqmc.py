@@ -64,7 +64,8 @@ class DQMC:
         l = self.l
         for which, m in ((_l.OP_HOP_HALF_B, l.chkr_hop_half[1]), (_l.OP_HOP_A, l.chkr_hop[0]),
                          (_l.OP_HOP_HALF_INV_B, l.chkr_hop_half_inv[1]), (_l.OP_HOP_INV_A, l.chkr_hop_inv[0]),
-                         (_l.OP_MU, l.chkr_mu), (_l.OP_MU_INV, l.chkr_mu_inv)):
+                         (_l.OP_MU, l.chkr_mu), (_l.OP_MU_INV, l.chkr_mu_inv),
+                         (_l.OP_HOP_HALF_A, l.chkr_hop_half[0]), (_l.OP_HOP_HALF_INV_A, l.chkr_hop_half_inv[0])):
             self._set_operator(which, m)
         nb = np.asfortranarray(l.neighbors.astype(np.int64))
         self._chk(self.lib.dqmc_set_neighbors(self._ctx, nb.ctypes.data_as(_l._I64)))
@@ -258,6 +259,38 @@ class DQMC:
         chi = np.zeros((nq, nq, nt), order="F")
         self._chk(self.lib.dqmc_measure_chi_dynamic(self._ctx, _l.dptr(chi)))
         return chi
+
+    # -- fermion_measurements.jl:1343-1541 --------------------------------------------------------------
+    def measure_tdgfs(self):
+        """`measure_tdgfs!`: G(tau,0) and G(0,tau) for all slices, kept on the device (read them with Gt0/G0t)."""
+        self._chk(self.lib.dqmc_measure_tdgfs(self._ctx))
+
+    def _tdgf(self, which, slc):
+        g = _l.cplx_buf((self.n, self.n))
+        self._chk(self.lib.dqmc_get_tdgf(self._ctx, which, int(slc), _l.dptr(g)))
+        return g
+
+    def Gt0(self, slc):
+        """`mc.s.meas.Gt0[slc]` (1-based slice)."""
+        return self._tdgf(0, slc)
+
+    def G0t(self, slc):
+        """`mc.s.meas.G0t[slc]` (1-based slice)."""
+        return self._tdgf(1, slc)
+
+    def deallocate_tdgfs_stacks(self):
+        self._chk(self.lib.dqmc_free_tdgfs(self._ctx))
+
+    def inv_sum_udts_scalettar(self, Ua, Da, Ta, Ub, Db, Tb):
+        """`inv_sum_udts_scalettar!` (linalg.jl:512-567) on host operands."""
+        n = self.n
+        res = _l.cplx_buf((n, n))
+        mats = [_l.cplx_in(x, (n, n)) for x in (Ua, Ta, Ub, Tb)]
+        da, db = np.ascontiguousarray(Da, dtype=np.float64), np.ascontiguousarray(Db, dtype=np.float64)
+        self._chk(self.lib.dqmc_inv_sum_udts(self._ctx, _l.dptr(mats[0]), _l.dptr(da), _l.dptr(mats[1]),
+                                             _l.dptr(mats[2]), _l.dptr(db), _l.dptr(mats[3]),
+                                             _l.dptr(res)))
+        return res
 
     def measure_chi_static(self):
         return float(self.measure_chi_dynamic()[0, 0, 0])

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdqmc_b200.so")
 
-OP_HOP_HALF_B, OP_HOP_A, OP_HOP_HALF_INV_B, OP_HOP_INV_A, OP_MU, OP_MU_INV = range(6)
+OP_HOP_HALF_B, OP_HOP_A, OP_HOP_HALF_INV_B, OP_HOP_INV_A, OP_MU, OP_MU_INV, OP_HOP_HALF_A, OP_HOP_HALF_INV_A = range(8)
 B_LEFT, B_RIGHT, B_INV_LEFT, B_INV_RIGHT, B_DAGGER_LEFT = range(5)
 
 
@@ -60,6 +60,10 @@ SIGNATURES = {
     "dqmc_calc_boson_action": (C.c_int, [_P, _D]),
     "dqmc_measure_chi_dynamic": (C.c_int, [_P, _D]),
     "dqmc_global_update": (C.c_int, [_P, C.c_double, _D, C.c_double, _D, _I32, _I32]),
+    "dqmc_measure_tdgfs": (C.c_int, [_P]),
+    "dqmc_get_tdgf": (C.c_int, [_P, C.c_int, C.c_int32, _D]),
+    "dqmc_free_tdgfs": (C.c_int, [_P]),
+    "dqmc_inv_sum_udts": (C.c_int, [_P, _D, _D, _D, _D, _D, _D, _D]),
     "dqmc_timers": (C.c_int, [_P, _D, C.c_int32]),
     "dqmc_set_timing": (C.c_int, [_P, C.c_int32]),
     "dqmc_checks": (C.c_int, [_P, _D, _I64]),

@@ -44,7 +44,9 @@ enum {
   DQMC_OP_HOP_INV_A = 3,       /* l.chkr_hop_inv[1]       */
   DQMC_OP_MU = 4,              /* l.chkr_mu               */
   DQMC_OP_MU_INV = 5,          /* l.chkr_mu_inv           */
-  DQMC_OP_COUNT = 6
+  DQMC_OP_HOP_HALF_A = 6,      /* l.chkr_hop_half[1]      (optional: only effective_greens2greens! needs it) */
+  DQMC_OP_HOP_HALF_INV_A = 7,  /* l.chkr_hop_half_inv[1]  (optional, same) */
+  DQMC_OP_COUNT = 8
 };
 
 /* dqmc_multiply_B op codes (slice_matrices.jl:101-226) */
@@ -108,6 +110,18 @@ int dqmc_measure_chi_dynamic(dqmc_ctx* ctx, double* chi);
  * (u[3], consumed only if p_acc <= 1); on rejection stack, G, logdet and field are restored from the backups. */
 int dqmc_global_update(dqmc_ctx* ctx, double box_global, const double* u, double S_old, double* S_new, int32_t* accepted,
                        int32_t* consumed);
+
+/* measure_tdgfs! (fermion_measurements.jl:1343-1407, with calc_Bchain_udts! :1434-1503, inv_sum_udts_scalettar! /
+ * inv_one_plus_udt_scalettar! linalg.jl:302-331,512-567, effective_greens2greens! :1125-1142 and fill_tdgf! :1509-1541):
+ * G(tau,0) and G(0,tau) for all M slices of the device-resident field, kept on the device (2 M n^2 ComplexF64 + four UDT
+ * chains; allocated on first use, released by dqmc_free_tdgfs = deallocate_tdgfs_stacks!). */
+int dqmc_measure_tdgfs(dqmc_ctx* ctx);
+/* mc.s.meas.Gt0[slice] (which = 0) or G0t[slice] (which = 1), slice 1-based, into a host n x n matrix */
+int dqmc_get_tdgf(dqmc_ctx* ctx, int which, int32_t slice, double* out);
+int dqmc_free_tdgfs(dqmc_ctx* ctx);
+/* inv_sum_udts_scalettar! (linalg.jl:512-567) of host operands: res = [Ua Da Ta + Ub Db Tb]^-1 */
+int dqmc_inv_sum_udts(dqmc_ctx* ctx, const double* Ua, const double* Da, const double* Ta, const double* Ub, const double* Db,
+                      const double* Tb, double* res);
 
 /* telemetry: phase times in ms (CUDA events): [0] wrap, [1] local updates, [2] stack UDT (add_slice_sequence),
  * [3] calculate_greens, [4] total of dqmc_sweep; resets the accumulators.  Replaces the @mytimeit labels

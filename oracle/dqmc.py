@@ -46,6 +46,7 @@ class OracleDQMC:
     def __init__(self, p, l=None, dense_hoppings=False):
         self.p = p
         self.l = l if l is not None else build_model(p, dense_hoppings=dense_hoppings)
+        self.dense_B = False         # True: CBFalse slice matrices (slice_matrices.jl:25-94), needs dense_hoppings
         self.N = self.l.sites
         self.n = p.flv * self.N
         self.hsfield = None          # [opdim, N, M] (Julia index order)
@@ -138,10 +139,21 @@ class OracleDQMC:
                          [0, -R, C, cS],
                          [R, 0, S, C]], dtype=complex)
 
+    # ---------------------------------------------------------------- slice_matrices.jl (no checkerboard)
+    def _dense_slice_matrix(self, slc, power):
+        """slice_matrices.jl:25-43 (CBFalse): e^{-dtau T/2} e^{-dtau T/2} e^{-dtau V} or its inverse."""
+        l = self.l
+        eV = self.interaction_matrix_exp(slc, power).toarray()
+        if power > 0:
+            return l.hopping_matrix_exp @ (l.hopping_matrix_exp @ eV)
+        return eV @ (l.hopping_matrix_exp_inv @ l.hopping_matrix_exp_inv)
+
     # ---------------------------------------------------------------- slice_matrices.jl (CBAssaad)
     def multiply_B_left(self, slc, M):
         """slice_matrices.jl:101-129: M <- hopB½ hopA hopB½ e^{dtau mu} e^{-dtau V} M."""
         l = self.l
+        if self.dense_B:
+            return self._dense_slice_matrix(slc, 1.0) @ M
         M = self.interaction_matrix_exp(slc, 1.0) @ M
         M = l.chkr_mu @ M
         M = l.chkr_hop_half[1] @ M
@@ -152,6 +164,8 @@ class OracleDQMC:
     def multiply_B_right(self, slc, M):
         """slice_matrices.jl:131-153: M <- M hopB½ hopA hopB½ e^{dtau mu} e^{-dtau V}."""
         l = self.l
+        if self.dense_B:
+            return M @ self._dense_slice_matrix(slc, 1.0)
         eV = self.interaction_matrix_exp(slc, 1.0)
         M = (l.chkr_hop_half[1].T @ M.T).T
         M = (l.chkr_hop[0].T @ M.T).T
@@ -163,6 +177,8 @@ class OracleDQMC:
     def multiply_B_inv_left(self, slc, M):
         """slice_matrices.jl:155-177: M <- e^{+dtau V} mu^-1 hopB½^-1 hopA^-1 hopB½^-1 M."""
         l = self.l
+        if self.dense_B:
+            return self._dense_slice_matrix(slc, -1.0) @ M
         eV = self.interaction_matrix_exp(slc, -1.0)
         M = l.chkr_hop_half_inv[1] @ M
         M = l.chkr_hop_inv[0] @ M
@@ -174,6 +190,8 @@ class OracleDQMC:
     def multiply_B_inv_right(self, slc, M):
         """slice_matrices.jl:179-201: M <- M e^{+dtau V} mu^-1 hopB½^-1 hopA^-1 hopB½^-1."""
         l = self.l
+        if self.dense_B:
+            return M @ self._dense_slice_matrix(slc, -1.0)
         eV = self.interaction_matrix_exp(slc, -1.0)
         M = (eV.T @ M.T).T
         M = (l.chkr_mu_inv.T @ M.T).T
@@ -185,6 +203,8 @@ class OracleDQMC:
     def multiply_daggered_B_left(self, slc, M):
         """slice_matrices.jl:203-226: M <- B(slice)^dagger M."""
         l = self.l
+        if self.dense_B:
+            return self._dense_slice_matrix(slc, 1.0).conj().T @ M
         eV = self.interaction_matrix_exp(slc, 1.0)
         M = l.chkr_hop_half_dagger[1] @ M
         M = l.chkr_hop_dagger[0] @ M
@@ -433,6 +453,126 @@ class OracleDQMC:
         self.boson_action = S_old
         self.u_stack, self.d_stack, self.t_stack, self.greens, self.log_det, self.hsfield = bk
         return 0
+
+    # ---------------------------------------------------------------- time-displaced Green's functions
+    def effective_greens2greens(self, G):
+        """fermion_measurements.jl:1125-1142 (CBTrue): G <- hop½_inv[1] hop½_inv[2] G hop½[2] hop½[1]
+        (the loops run over reverse(1:n_groups)); :1178-1185 for the dense (CBFalse) hoppings."""
+        l = self.l
+        if self.dense_B:
+            return l.hopping_matrix_exp_inv @ (G @ l.hopping_matrix_exp)
+        for i in reversed(range(len(l.chkr_hop_half))):
+            G = (l.chkr_hop_half[i].T @ G.T).T
+        for i in reversed(range(len(l.chkr_hop_half_inv))):
+            G = l.chkr_hop_half_inv[i] @ G
+        return G
+
+    def calc_Bchain_udts(self, invert=False, left=True):
+        """fermion_measurements.jl:1434-1503 ``calc_Bchain_udts!``: UDTs at the safe_mult slices of
+        left,  invert=False:  B(tau,1)      = B(tau) ... B(1)            (udt[i]: slices 1..ranges[i][end])
+        left,  invert=True :  B(tau,1)^-1   = B(1)^-1 ... B(tau)^-1
+        right, invert=False:  B(beta,tau)   = B(beta) ... B(tau)         (udt[i]: slices ranges[i][1]..M)
+        right, invert=True :  B(beta,tau)^-1 = B(tau)^-1 ... B(beta)^-1
+        Returns (u_stack, d_stack, t_stack) with K = M/safe_mult entries, already reversed for dir = RIGHT."""
+        n, K = self.n, len(self.ranges)
+        us, ds, ts = [None] * K, [None] * K, [None] * K
+        rightmult = (not left and not invert) or (left and invert)
+        rng = range(K) if left else reversed(range(K))
+        for i, ridx in enumerate(rng):
+            if i == 0:
+                cur = np.eye(n, dtype=complex)
+            else:
+                cur = (ts[i - 1] if rightmult else us[i - 1]).copy()
+            srange = self.ranges[ridx] if left else reversed(self.ranges[ridx])
+            for slc in srange:
+                if not invert:
+                    cur = self.multiply_B_left(slc, cur) if left else self.multiply_B_right(slc, cur)
+                else:
+                    cur = self.multiply_B_inv_right(slc, cur) if left else self.multiply_B_inv_left(slc, cur)
+            if i != 0:
+                cur = ds[i - 1][:, None] * cur if rightmult else cur * ds[i - 1][None, :]
+            U, D, T = decompose_udt(cur)
+            ds[i] = D
+            if not rightmult:
+                us[i] = U
+                ts[i] = T if i == 0 else T @ ts[i - 1]
+            else:
+                ts[i] = T
+                us[i] = U if i == 0 else us[i - 1] @ U
+        if not left:
+            us.reverse(); ds.reverse(); ts.reverse()
+        return us, ds, ts
+
+    @staticmethod
+    def inv_one_plus_udt_scalettar(U, D, T):
+        """linalg.jl:302-331: [1 + U D T]^-1 with scales above and below one separated and two intermediate UDTs."""
+        Dpinv = 1.0 / np.maximum(D, 1.0)
+        Dm = np.minimum(D, 1.0)
+        l = sla.solve(T, np.diag(Dpinv).astype(complex), check_finite=False)
+        r = U * Dm[None, :] + l
+        u, d, t = decompose_udt(r)
+        r = sla.solve(t, np.diag(1.0 / d).astype(complex), check_finite=False)
+        l = Dpinv[:, None] * (r @ u.conj().T)
+        u, d, t = decompose_udt(l)
+        l = sla.solve(T, u, check_finite=False)
+        return (l * d[None, :]) @ t
+
+    @staticmethod
+    def inv_sum_udts_scalettar(Ua, Da, Ta, Ub, Db, Tb):
+        """linalg.jl:512-567: [Ua Da Ta + Ub Db Tb]^-1, same scale separation."""
+        Dap, Dam = np.maximum(Da, 1.0), np.minimum(Da, 1.0)
+        Dbp, Dbm = np.maximum(Db, 1.0), np.minimum(Db, 1.0)
+        mat1 = sla.solve(Tb.T, Ta.T, check_finite=False).T           # Ta / Tb
+        mat1 = mat1 * (Dam[:, None] / Dbp[None, :])
+        mat2 = (Ua.conj().T @ Ub) * (Dbm[None, :] / Dap[:, None])
+        U, D, T = decompose_udt(mat1 + mat2)
+        mat1 = sla.solve(D[:, None] * T, U.conj().T, check_finite=False)
+        mat1 = mat1 / Dbp[:, None] / Dap[None, :]
+        U, D, T = decompose_udt(mat1)
+        U = sla.solve(Tb, U, check_finite=False)
+        T = T @ Ua.conj().T
+        return (U * D[None, :]) @ T
+
+    def measure_tdgfs(self):
+        """fermion_measurements.jl:1343-1407 ``measure_tdgfs!``: Gt0[tau] = G(tau,0), G0t[tau] = G(0,tau) for all M slices
+        (0-based tau here): stabilised at the safe_mult slices, B-propagated in between (``fill_tdgf!`` :1509-1541)."""
+        M, sm = self.p.slices, self.p.safe_mult
+        n = self.n
+        Gt0 = np.zeros((M, n, n), dtype=complex)
+        G0t = np.zeros((M, n, n), dtype=complex)
+        BT0Inv = self.calc_Bchain_udts(invert=True, left=True)
+        BBetaT = self.calc_Bchain_udts(invert=False, left=False)
+        BT0 = self.calc_Bchain_udts(invert=False, left=True)
+        BBetaTInv = self.calc_Bchain_udts(invert=True, left=False)
+        self.tdgf_stacks = dict(BT0Inv=BT0Inv, BBetaT=BBetaT, BT0=BT0, BBetaTInv=BBetaTInv)
+        for i, tau in enumerate(range(0, M, sm)):
+            if i != 0:
+                g = self.inv_sum_udts_scalettar(BT0Inv[0][i - 1], BT0Inv[1][i - 1], BT0Inv[2][i - 1],
+                                                BBetaT[0][i], BBetaT[1][i], BBetaT[2][i])
+                Gt0[tau] = self.effective_greens2greens(g)
+                g = self.inv_sum_udts_scalettar(BT0[0][i - 1], BT0[1][i - 1], BT0[2][i - 1],
+                                                BBetaTInv[0][i], BBetaTInv[1][i], BBetaTInv[2][i])
+                G0t[tau] = self.effective_greens2greens(g)
+            else:
+                Gt0[tau] = self.effective_greens2greens(self.inv_one_plus_udt_scalettar(BBetaT[0][0], BBetaT[1][0], BBetaT[2][0]))
+                G0t[tau] = self.effective_greens2greens(
+                    self.inv_one_plus_udt_scalettar(BBetaTInv[0][0], BBetaTInv[1][0], BBetaTInv[2][0]))
+        # fill_tdgf!: reference (1-based) Mhalf = M/2+1; tau in Mhalf:M forward, (Mhalf-1):-1:1 backward
+        safe = set(range(0, M, sm))
+        mhalf = M // 2              # 0-based index of reference slice Mhalf
+        for tau in range(mhalf, M):
+            if tau in safe:
+                continue
+            Gt0[tau] = self.multiply_B_left(tau, Gt0[tau - 1].copy())
+            G0t[tau] = self.multiply_B_inv_right(tau, G0t[tau - 1].copy())
+        for tau in range(mhalf - 1, -1, -1):
+            if tau in safe:
+                continue
+            Gt0[tau] = self.multiply_B_inv_left(tau + 1, Gt0[tau + 1].copy())
+            G0t[tau] = self.multiply_B_right(tau + 1, G0t[tau + 1].copy())
+        G0t *= -1.0
+        self.Gt0, self.G0t = Gt0, G0t
+        return Gt0, G0t
 
     # ---------------------------------------------------------------- helpers used by the reference's tests
     def calc_greens_fresh(self, slc):

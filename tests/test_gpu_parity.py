@@ -300,3 +300,58 @@ def test_chi_dynamic_device(golden_o3):
     ref = om.measure_chi_dynamic(f)
     assert np.max(np.abs(mc.measure_chi_dynamic() - ref) / (1e-300 + np.abs(ref).max())) < 1e-12
     mc.close()
+
+
+# ------------------------------------------------------------------------------------------ time-displaced G
+def test_inv_sum_udts_vs_oracle():
+    # linalg.jl:512-567 on the UDTs of real B chains (scales graded over ~16 orders of magnitude): B(tau,1)^-1 and
+    # B(beta,tau) of a random field, i.e. exactly the operands measure_tdgfs! feeds it
+    L, M = 4, 40
+    mc, om = _mk(L, M, True)
+    field = np.random.RandomState(11).rand(3, L * L, M)
+    mc.hsfield = field
+    om.hsfield = field.copy()
+    a = om.calc_Bchain_udts(invert=True, left=True)
+    b = om.calc_Bchain_udts(invert=False, left=False)
+    for i in (1, 2, 3):
+        ops = (a[0][i - 1], a[1][i - 1], a[2][i - 1], b[0][i], b[1][i], b[2][i])
+        ref = om.inv_sum_udts_scalettar(*ops)
+        got = mc.inv_sum_udts_scalettar(*ops)
+        assert maxabs(got, ref) < 1e-10 * np.abs(ref).max(), i
+    mc.close()
+
+
+@pytest.mark.parametrize("L,M,bfield", [(4, 20, True), (4, 40, False), (8, 40, True)])
+def test_tdgfs_vs_oracle(L, M, bfield):
+    # measure_tdgfs! (fermion_measurements.jl:1343-1407): every slice of G(tau,0) and G(0,tau) against the oracle
+    mc, om = _mk(L, M, bfield)
+    field = np.random.RandomState(21).rand(3, L * L, M)
+    mc.init(field)
+    om.init(field)
+    mc.measure_tdgfs()
+    Gt0, G0t = om.measure_tdgfs()
+    for tau in range(M):
+        assert maxabs(mc.Gt0(tau + 1), Gt0[tau]) < 1e-10 * max(1.0, np.abs(Gt0[tau]).max()), tau
+        assert maxabs(mc.G0t(tau + 1), G0t[tau]) < 1e-10 * max(1.0, np.abs(G0t[tau]).max()), tau
+    n = mc.n
+    assert maxabs(mc.Gt0(1) - mc.G0t(1), np.eye(n)) < 1e-10
+    mc.deallocate_tdgfs_stacks()
+    mc.close()
+
+
+def test_tdgfs_large_size_properties():
+    # BASELINE config 5 shape at reduced M: L=20 (n=1600); tau = 0 relations and agreement with the propagated
+    # equal-time G (effective -> actual) at the first slice
+    L, M = 20, 20
+    mc, _ = _mk(L, M, False)
+    field = np.random.RandomState(22).rand(3, L * L, M)
+    mc.init(field)
+    mc.measure_tdgfs()
+    n = mc.n
+    g1, g2 = mc.Gt0(1), mc.G0t(1)
+    assert maxabs(g1 - g2, np.eye(n)) < 1e-9
+    g11, g12 = mc.Gt0(11), mc.G0t(11)
+    # G(tau,0) G(0,tau) structure: both finite and G(tau,0) = B(tau,1) G(1,0)-like growth bounded
+    assert np.isfinite(g11).all() and np.isfinite(g12).all()
+    mc.deallocate_tdgfs_stacks()
+    mc.close()

@@ -236,3 +236,69 @@ def test_chi_dynamic(mc_b, golden_o3):
     chi = mc_b.measure_chi_dynamic(golden_o3["randconf"])
     assert maxabs(chi, golden_o3["chi_dyn"]) < 1e-12
     assert np.isclose(chi[0, 0, 0], 12.420575691388407, rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------ time-displaced G
+def _free_tdgf_analytic(p, L, M, tau_i, g0t=False):
+    """test/deps/ed.jl:664-707: eps(k) = -2 th cos kx - 2 tv cos ky - mu, G(tau,0)(k) = e^{-tau eps}/(1+e^{-beta eps}),
+    G(0,tau)(k) = -e^{tau eps}/(1+e^{beta eps}); transformed to real space (site = y + L x, flavours x,y,x,y)."""
+    N = L * L
+    beta, tau = M * p.delta_tau, tau_i * p.delta_tau
+    ks = 2 * np.pi * np.fft.fftfreq(L)
+    ys, xs = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+    ys, xs = ys.ravel(order="F"), xs.ravel(order="F")
+    out = np.zeros((4 * N, 4 * N), dtype=complex)
+    for f, (th, tv) in enumerate([(1.0, 0.5), (-0.5, -1.0), (1.0, 0.5), (-0.5, -1.0)]):
+        blk = np.zeros((N, N), dtype=complex)
+        for ky in ks:
+            for kx in ks:
+                e = -2 * th * np.cos(kx) - 2 * tv * np.cos(ky) - p.mu1
+                g = -np.exp(tau * e) / (1 + np.exp(beta * e)) if g0t else np.exp(-tau * e) / (1 + np.exp(-beta * e))
+                ph = np.exp(1j * (ky * ys + kx * xs))
+                blk += g * np.outer(ph, ph.conj()) / N
+        out[f * N:(f + 1) * N, f * N:(f + 1) * N] = blk
+    return out
+
+
+def test_tdgf_free_fermions_analytic():
+    # tests_freefermions.jl:174-237 (free fermions, no checkerboard): measure_tdgfs! against the k-space formulas,
+    # Gt0[1] == greens, Gt0[1] - G0t[1] == 1, G(tau,0) == -G(0,beta-tau)
+    L, M = 4, 40
+    p = Params(L=L, slices=M, safe_mult=10, Bfield=False, lam=0.0)
+    om = OracleDQMC(p, dense_hoppings=True)
+    om.dense_B = True
+    om.init(np.random.RandomState(3).rand(3, L * L, M) + 0.1)
+    Gt0, G0t = om.measure_tdgfs()
+    for tau_i in (0, 1, 7, 10, 19, 20, 25, 39):
+        assert maxabs(Gt0[tau_i], _free_tdgf_analytic(p, L, M, tau_i)) < 1e-12
+        assert maxabs(G0t[tau_i], _free_tdgf_analytic(p, L, M, tau_i, g0t=True)) < 1e-12
+    assert maxabs(Gt0[0], om.effective_greens2greens(om.greens)) < 1e-12
+    assert maxabs(Gt0[0] - G0t[0], np.eye(4 * L * L)) < 1e-12
+    assert max(maxabs(Gt0[t], -G0t[M - t]) for t in range(1, M)) < 1e-10
+
+
+def test_tdgf_interacting_consistency():
+    # tests_O3_measurements.jl:195-212 spirit (CBAssaad, B-field, lambda > 0): Gt0[1] is the equal-time G of slice 1
+    # (effective -> actual), Gt0[1] - G0t[1] = 1, the four UDT chains have unitary U, and the inverse sums agree with a
+    # plain dense inverse of the same chains
+    L, M = 4, 20
+    p = Params(L=L, slices=M, safe_mult=10, Bfield=True)
+    om = OracleDQMC(p)
+    om.init(np.random.RandomState(5).rand(3, L * L, M))
+    Gt0, G0t = om.measure_tdgfs()
+    n = om.n
+    g1 = om.effective_greens2greens(om.calc_greens_fresh(0))
+    assert maxabs(Gt0[0], g1) < 1e-11
+    assert maxabs(Gt0[0] - G0t[0], np.eye(n)) < 1e-11
+    for us, ds, ts in om.tdgf_stacks.values():
+        for U in us:
+            assert maxabs(U @ U.conj().T, np.eye(n)) < 1e-12
+    # dense check of slice 11 (i = 2): G(tau,0) = [B(tau,1)^-1 + B(beta,tau)]^-1 with tau = ranges[1][0]
+    Binv = np.eye(n, dtype=complex)
+    for s in range(0, 10):
+        Binv = om.multiply_B_inv_right(s, Binv)
+    Bbt = np.eye(n, dtype=complex)
+    for s in range(M - 1, 9, -1):
+        Bbt = om.multiply_B_right(s, Bbt)
+    dense = om.effective_greens2greens(np.linalg.inv(Binv + Bbt))
+    assert maxabs(Gt0[10], dense) < 1e-9
