@@ -507,8 +507,17 @@ static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
   const int n = c->n;
   TRY(c, argsort_desc(c->st, c->colnorm, n, c->perm));
   TRY(c, gather_cols(c->st, c->W[0], n, n, c->perm, c->W[1], n, c->num_sms));
-  TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, nullptr, 0, 0, c->num_sms, c->lookahead ? &c->qra : nullptr));
-  TRY(c, qr_form_q(c->st, c->W[1], n, n, c->tfac, Uout, n, c->num_sms));
+  // Q^H is accumulated on the second stream while the (latency-bound) panel chain runs: Q^H = H_k^H ... H_1^H 1 is the
+  // "right-hand side" of the factorization; U = (Q^H)^H afterwards.  (Forming Q by backward accumulation after the
+  // factorization costs half the flops but cannot overlap with anything.)
+  if (c->lookahead) {
+    TRY(c, set_identity(c->st, c->W[0], n, n, c->num_sms));
+    TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, c->W[0], n, n, c->num_sms, &c->qra));
+    TRY(c, ew_combine(c->st, n, EwTerm{c->W[0], 1, nullptr, 0, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, 1.0, Uout, c->num_sms));
+  } else {
+    TRY(c, qr_factor(c->st, c->W[1], n, n, c->tau, Dout, c->tfac, nullptr, 0, 0, c->num_sms, nullptr));
+    TRY(c, qr_form_q(c->st, c->W[1], n, n, c->tfac, Uout, n, c->num_sms));
+  }
   TRY(c, build_T(c->st, c->W[1], n, n, Dout, c->perm, c->W[2], n, c->num_sms));
   return 0;
 }
