@@ -318,15 +318,15 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
 
   for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) Tsm[e % QR_NB][e / QR_NB] = T[e];
 
-  // ---- phase 1: W = V^H C   (32 x 8), K = m split over the 8 warps
+  // ---- phase 1: W = V^H C   (32 x 8), K = m split over the 8 warps; the fragments of the next 8-row step are
+  // loaded (L2 latency) while the DMMAs of the current one run
   double cr[4][2], ci[4][2];
 #pragma unroll
   for (int it = 0; it < 4; ++it) cr[it][0] = cr[it][1] = ci[it][0] = ci[it][1] = 0.0;
   const int kchunk = (((m + 7) / 8) + 3) / 4 * 4;
   const int kbeg = warp * kchunk, kend = min(m, kbeg + kchunk);
   const bool colok = (c0 + lo) < ncols;
-  for (int r0 = kbeg; r0 < kend; r0 += 8) {
-    cplx av[2][4], bv[2];
+  auto load_step = [&](int r0, cplx (&av)[2][4], cplx (&bv)[2]) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int r = r0 + 4 * u + lk;
@@ -337,6 +337,8 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
       }
       bv[u] = (r < kend && colok) ? C[(size_t)(c0 + lo) * ldc + r] : cmake(0.0, 0.0);
     }
+  };
+  auto mma_step = [&](const cplx (&av)[2][4], const cplx (&bv)[2]) {
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -346,6 +348,20 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
         dmma884(ci[it][0], ci[it][1], av[u][it].x, bv[u].y);
         dmma884(ci[it][0], ci[it][1], -av[u][it].y, bv[u].x);
       }
+  };
+  {
+    cplx avA[2][4], bvA[2], avB[2][4], bvB[2];
+    int r0 = kbeg;
+    if (r0 < kend) load_step(r0, avA, bvA);
+    while (r0 < kend) {
+      if (r0 + 8 < kend) load_step(r0 + 8, avB, bvB);
+      mma_step(avA, bvA);
+      r0 += 8;
+      if (r0 >= kend) break;
+      if (r0 + 8 < kend) load_step(r0 + 8, avA, bvA);
+      mma_step(avB, bvB);
+      r0 += 8;
+    }
   }
   if (warp >= 4) {
 #pragma unroll
@@ -381,16 +397,23 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
     W2[i][c] = acc;
   }
   __syncthreads();
-  // ---- phase 3: C -= V W   (m x 8), K = 32
+  // ---- phase 3: C -= V W   (m x 8), K = 32; next tile's V fragments and C values prefetched
   const int ntile = (m + 7) / 8;
-  for (int rt = warp; rt < ntile; rt += 8) {
+  auto load_tile = [&](int rt, cplx (&av)[8], cplx (&cv)[2]) {
     const int r = rt * 8 + lo;
-    cplx av[8];
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int c = kk * 4 + lk;
       av[kk] = (rt * 8 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c);
     }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = c0 + 2 * lk + e;
+      cv[e] = (r < m && col < ncols) ? C[(size_t)col * ldc + r] : cmake(0.0, 0.0);
+    }
+  };
+  auto do_tile = [&](int rt, const cplx (&av)[8], const cplx (&cv)[2]) {
+    const int r = rt * 8 + lo;
     double dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
@@ -403,12 +426,21 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int col = c0 + 2 * lk + e;
-      if (r < m && col < ncols) {
-        cplx* p = C + (size_t)col * ldc + r;
-        cplx t = *p;
-        t.x -= dr[e]; t.y -= di[e];
-        *p = t;
-      }
+      if (r < m && col < ncols) C[(size_t)col * ldc + r] = cmake(cv[e].x - dr[e], cv[e].y - di[e]);
+    }
+  };
+  {
+    cplx avA[8], cvA[2], avB[8], cvB[2];
+    int rt = warp;
+    if (rt < ntile) load_tile(rt, avA, cvA);
+    while (rt < ntile) {
+      if (rt + 8 < ntile) load_tile(rt + 8, avB, cvB);
+      do_tile(rt, avA, cvA);
+      rt += 8;
+      if (rt >= ntile) break;
+      if (rt + 8 < ntile) load_tile(rt + 8, avA, cvA);
+      do_tile(rt, avB, cvB);
+      rt += 8;
     }
   }
 }
