@@ -159,7 +159,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   c->sm = p->safe_mult;
   c->nel = c->M / c->sm + 1;
   c->kmax = p->delay > 0 ? p->delay : 16;
-  if (c->kmax > 32) c->kmax = 32;
+  if (c->kmax > 16) c->kmax = 16;   // the flush stages at most two k-chunks of 32 columns
   c->have_nbr = c->ops_ready = false;
   c->timing = false;
   for (int i = 0; i < TM_COUNT; ++i) c->tacc[i] = 0.0;
@@ -210,6 +210,11 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->d_action, 1 + 1024));
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
+  {   // the batch depth is halved until the kernel's shared memory fits (large lattices)
+    LUArgs probe; probe.nsites = c->N; probe.rpc = c->lu_rpc;
+    for (probe.kmax = c->kmax; probe.kmax > 2 && local_updates_smem(probe) > (size_t)210 * 1024; probe.kmax /= 2) { }
+    c->kmax = probe.kmax;
+  }
   CU(c, cudaStreamSynchronize(c->st));
   *out = c;
   return 0;
@@ -1048,7 +1053,7 @@ extern "C" int dqmc_lu_profile(dqmc_ctx* c, int32_t enable, int64_t* out16) {
   CU(c, cudaSetDevice(c->p.device));
   c->lu_prof = enable != 0;
   if (out16) {
-    CU(c, cudaMemcpyAsync(out16, c->d_prof, sizeof(long long) * 24, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(out16, c->d_prof, sizeof(long long) * 32, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
   }
   return 0;

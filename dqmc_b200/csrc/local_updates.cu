@@ -48,6 +48,12 @@ __device__ __forceinline__ cplx ld_cg_issue(const cplx* p) {
 }
 __device__ __forceinline__ cplx ldcg2(const cplx* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
+__device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gmem_src, bool pred) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 16 : 0;   // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+
 // 4x4 complex e^{-power*dtau*V(op)} (interactions.jl:102-141), element (r,c):  [C S 0 R; cS C -R 0; 0 -R C cS; R 0 S C]
 __device__ __forceinline__ cplx evop_elem(int r, int c, double C, cplx S, double R) {
   if (r == c) return cmake(C, 0.0);
@@ -182,8 +188,8 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   cplx* Bs4 = sp; sp += 2 * 4 * lds;                        // [2][4][ldk] cols site+kN of B
   cplx* gcol = sp; sp += (size_t)2 * rpc * 4;               // [2][rpc][4] G[r, site+kN] for my rows
   cplx* grow = sp; sp += (size_t)2 * rpc * 4;               // [2][rpc][4] G[site+kN, c] for my cols
-  cplx* FA = sp; sp += 64 * 36;                             // flush staging: 64 rows x 32 k (+4 pad)
-  cplx* FB = sp; sp += 64 * 36;
+  cplx* FA = sp; sp += 2 * 64 * 36;                         // flush staging: 2 k-chunks x 64 rows x 32 k (+4 pad)
+  cplx* FB = sp; sp += 2 * 64 * 36;
   double* fs = reinterpret_cast<double*>(sp);               // [3N] field of this slice
   double* tn = fs + 3 * N;                                  // [3N] phi(l+1) + phi(l-1)
   double* uw = tn + 3 * N;                                  // [4N] this slice's window of the uniform stream
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   __shared__ long long stampA[8], stampB[8], stampP[8];
   __shared__ long long p_role[8], p_role1[8];
   if (tid < 8) { p_role[tid] = 0; p_role1[tid] = 0; }
+  long long pf[3] = {0, 0, 0};
   long long p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
   __syncthreads();
   const long long t_begin = clock64();
@@ -468,56 +475,33 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     const bool do_flush = (kc == a.kmax || (i == N - 1 && kc > 0));
     if (do_flush) {
       n_fl++;
+      long long tf0 = clock64();
       grid_barrier(a.bar, gridDim.x);
+      long long tf1 = clock64();
       const int K = 4 * kc;
       const int lo = lane >> 2, lk = lane & 3;
       const int wm = warp & 1, wn = warp >> 1;           // 2 x 4 warps, warp tile 32 x 16
       const int tiles_m = (n + 63) / 64, ntiles = tiles_m * tiles_m;
+      const int nch = (K + 31) / 32;                     // k-chunks of 32 (at most kmax*4/32)
+      // operands staged with cp.async, one commit group per k-chunk (A and B together); a CTA's tiles that share their
+      // row block keep the A chunks; the G tile is fetched into registers before the DMMAs start
+      int tm_loaded = -1;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int tm0 = (t % tiles_m) * 64, tn0 = (t / tiles_m) * 64;
-        double cr[4][2][2], ci[4][2][2];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 2; ++y) cr[x][y][0] = cr[x][y][1] = ci[x][y][0] = ci[x][y][1] = 0.0;
-        cplx ra[8], rb[8];
-        auto stage_load = [&](int k0) {
+        const bool loadA = (tm0 != tm_loaded);
+        tm_loaded = tm0;
+        for (int ch = 0; ch < nch; ++ch) {
+          const int k0 = ch * 32;
+          cplx* fa = FA + ch * (64 * 36);
+          cplx* fb = FB + ch * (64 * 36);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int e = tid + 256 * u, rr = e >> 5, kk = e & 31;
             const bool kok = (k0 + kk) < K;
-            ra[u] = (kok && tm0 + rr < n) ? ldcg2(Atb + (size_t)(tm0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
-            rb[u] = (kok && tn0 + rr < n) ? ldcg2(Bmb + (size_t)(tn0 + rr) * ldk + k0 + kk) : cmake(0.0, 0.0);
+            if (loadA) { const bool ok = kok && tm0 + rr < n; cp_async16(fa + rr * 36 + kk, ok ? Atb + (size_t)(tm0 + rr) * ldk + k0 + kk : Atb, ok); }
+            { const bool ok = kok && tn0 + rr < n; cp_async16(fb + rr * 36 + kk, ok ? Bmb + (size_t)(tn0 + rr) * ldk + k0 + kk : Bmb, ok); }
           }
-        };
-        stage_load(0);
-        for (int k0 = 0; k0 < K; k0 += 32) {
-          __syncthreads();
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = tid + 256 * u, rr = e >> 5, kk = e & 31;
-            FA[rr * 36 + kk] = ra[u];
-            FB[rr * 36 + kk] = rb[u];
-          }
-          __syncthreads();
-          if (k0 + 32 < K) stage_load(k0 + 32);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            cplx av[4], bv[2];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) av[x] = FA[(wm * 32 + x * 8 + lo) * 36 + ks * 4 + lk];
-#pragma unroll
-            for (int y = 0; y < 2; ++y) bv[y] = FB[(wn * 16 + y * 8 + lo) * 36 + ks * 4 + lk];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-              for (int y = 0; y < 2; ++y) {
-                dmma884(cr[x][y][0], cr[x][y][1], av[x].x, bv[y].x);
-                dmma884(cr[x][y][0], cr[x][y][1], -av[x].y, bv[y].y);
-                dmma884(ci[x][y][0], ci[x][y][1], av[x].x, bv[y].y);
-                dmma884(ci[x][y][0], ci[x][y][1], av[x].y, bv[y].x);
-              }
-          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
         }
         cplx gv[4][2][2];
 #pragma unroll
@@ -529,6 +513,36 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
               gv[x][y][e] = (row < n && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
             }
+        double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 2; ++y) cr[x][y][0] = cr[x][y][1] = ci[x][y][0] = ci[x][y][1] = 0.0;
+        for (int ch = 0; ch < nch; ++ch) {
+          if (ch + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncthreads();
+          const cplx* fa = FA + ch * (64 * 36);
+          const cplx* fb = FB + ch * (64 * 36);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            cplx av[4], bv[2];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) av[x] = fa[(wm * 32 + x * 8 + lo) * 36 + ks * 4 + lk];
+#pragma unroll
+            for (int y = 0; y < 2; ++y) bv[y] = fb[(wn * 16 + y * 8 + lo) * 36 + ks * 4 + lk];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+              for (int y = 0; y < 2; ++y) {
+                dmma884(cr[x][y][0], cr[x][y][1], av[x].x, bv[y].x);
+                dmma884(cr[x][y][0], cr[x][y][1], -av[x].y, bv[y].y);
+                dmma884(ci[x][y][0], ci[x][y][1], av[x].x, bv[y].y);
+                dmma884(ci[x][y][0], ci[x][y][1], av[x].y, bv[y].x);
+              }
+          }
+        }
+        __syncthreads();                                   // staging buffers free for the next tile's loads
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -540,7 +554,10 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
                 a.G[(size_t)col * n + row] = cmake(gv[x][y][e].x + cr[x][y][e], gv[x][y][e].y + ci[x][y][e]);
             }
       }
+      long long tf2 = clock64();
       grid_barrier(a.bar, gridDim.x);
+      long long tf3 = clock64();
+      if (prof && tid == 0) { pf[0] += tf1 - tf0; pf[1] += tf2 - tf1; pf[2] += tf3 - tf2; }
       {   // re-arm my rows of the buffer just consumed (nobody reads it again before the flush after next)
         cplx* Atw = a.At + batch * bufstride;
         cplx* Bmw = a.Bm + batch * bufstride;
@@ -576,6 +593,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     a.prof[0] = clock64() - t_begin; a.prof[1] = p_s1; a.prof[2] = p_rest_acc; a.prof[3] = p_flush; a.prof[4] = n_fl;
     a.prof[5] = nacc; a.prof[6] = p_rest_rej;
     for (int w = 0; w < 8; ++w) { a.prof[8 + w] = p_role[w]; a.prof[16 + w] = p_role1[w]; }
+    a.prof[24] = pf[0]; a.prof[25] = pf[1]; a.prof[26] = pf[2];
   }
 
   if (blockIdx.x == 0 && tid == 0) {
@@ -600,7 +618,7 @@ int local_updates_grid(int n, int num_sms, int* rpc) {
 size_t local_updates_smem(const LUArgs& a) {
   const int ldk = 4 * a.kmax;
   const int lds = ldk + 2;
-  return sizeof(cplx) * ((size_t)2 * a.rpc * lds + 16 * lds + 16 * a.rpc + 2 * 64 * 36) + sizeof(double) * 10 * a.nsites +
+  return sizeof(cplx) * ((size_t)2 * a.rpc * lds + 16 * lds + 16 * a.rpc + 4 * 64 * 36) + sizeof(double) * 10 * a.nsites +
          sizeof(int) * 4 * a.nsites;
 }
 

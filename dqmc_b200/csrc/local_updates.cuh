@@ -27,3 +27,4 @@ struct LUArgs {
 
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid);
 int local_updates_grid(int n, int num_sms, int* rpc);
+size_t local_updates_smem(const LUArgs& a);

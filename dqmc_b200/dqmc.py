@@ -360,7 +360,7 @@ class DQMC:
         return ms.value
 
     def lu_profile(self, enable=True, read=False):
-        out = np.zeros(24, dtype=np.int64)
+        out = np.zeros(32, dtype=np.int64)
         self._chk(self.lib.dqmc_lu_profile(self._ctx, int(enable), out.ctypes.data_as(_l._I64) if read else None))
         return out
 

@@ -143,8 +143,9 @@ int dqmc_bench_kernel(dqmc_ctx* ctx, int which, int reps, double* ms_per_launch)
 int dqmc_test_zgemm(dqmc_ctx* ctx, int opA, int opB, int M, int N, int K, const double* alpha, const double* A, int lda,
                     const double* B, int ldb, const double* beta, double* C, int ldc);
 /* cycle counters of the last local_updates launch: [0] total, [1] stage 1, [2] stage 2, [3] flush, [4] #flushes,
- * [5] accepts, [8..15] per-warp stage-1 time, [16..23] per-warp role time before the speculative part (debug; 24 values) */
-int dqmc_lu_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out24);
+ * [5] accepts, [8..15] per-warp stage-1 time, [16..23] per-warp role time before the speculative part,
+ * [24..26] flush: first grid barrier, tiles, second grid barrier (debug; 32 values) */
+int dqmc_lu_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out32);
 /* per-phase cycle counters of the QR panel kernel accumulated since the last call (debug) */
 int dqmc_qr_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out8);
 int64_t dqmc_kernel_launches(dqmc_ctx* ctx);   /* kernels launched by this context so far */

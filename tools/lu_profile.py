@@ -21,3 +21,4 @@ print(" per-site stage1 %.0f cyc; per-accept stage2 %.0f cyc; per-reject tail %.
 print(" role cycles/site: decision %.0f  prep %s  prefetch %s" % (p[8]/N, [int(p[9+k]/N) for k in range(3)], [int(p[12+k]/N) for k in range(4)]))
 mc.close()
 print(" role-only cycles/site (before the speculative dot products): %s" % [int(p[16+k]/N) for k in range(8)])
+print(" per flush: barrier-1 %.0f, tiles %.0f, barrier-2 %.0f cycles" % tuple(p[24+k]/max(p[4],1) for k in range(3)))
