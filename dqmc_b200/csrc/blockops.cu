@@ -1,5 +1,10 @@
 #include "blockops.cuh"
 
+__device__ __forceinline__ void cp_async_16(cplx* smem_dst, const cplx* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // One CTA stages `nvec` vectors of length n (columns for COLS, rows for ROWS) in shared memory,
 // applies every step of the chain in place, and writes them back.
 template <bool ROWS>
@@ -18,35 +23,68 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
   const int nvec = min(nvec_cta, n - v0);
   const int tid = threadIdx.x;
 
-  // ---- global -> shared
+  // ---- global -> shared: 16-byte cp.async copies, all in flight at once (no register round trip, no per-load stall)
   if (!ROWS) {
     for (int v = 0; v < nvec; ++v)
-      for (int j = tid; j < n; j += blockDim.x) x[(size_t)v * ldx + j] = mat[(size_t)(v0 + v) * ld + j];
+      for (int j = tid; j < n; j += blockDim.x) cp_async_16(x + (size_t)v * ldx + j, mat + (size_t)(v0 + v) * ld + j);
   } else {
     // element (row v0+v, col j): v fastest so that each column contributes nvec*16 contiguous bytes
     const int tot = nvec * n;
     for (int e = tid; e < tot; e += blockDim.x) {
       int v = e % nvec, j = e / nvec;
-      x[(size_t)v * ldx + j] = mat[(size_t)j * ld + v0 + v];
+      cp_async_16(x + (size_t)v * ldx + j, mat + (size_t)j * ld + v0 + v);
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
+  // the 4x4 block of the NEXT stored-operator step is fetched (L2 latency) while the current step runs; with n/4 <= 256
+  // blocks every thread owns exactly one block per step
+  cplx mnx[4][4];
+  int inx[4] = {0, 0, 0, 0};
+  auto prefetch_block = [&](int st) {
+    if (st >= chain.nsteps) return;
+    const ChainStep& s = chain.s[st];
+    if (s.kind != 0 || tid >= s.nblk) return;
+    const cplx* vp = s.val + 16 * (size_t)tid;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        cplx t = (s.mode == OP_N || s.mode == OP_J) ? vp[4 * r + c] : vp[4 * c + r];
+        if (s.mode == OP_C || s.mode == OP_J) t.y = -t.y;
+        mnx[r][c] = t;
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) inx[k] = s.idx[4 * tid + k];
+  };
+  prefetch_block(0);
   for (int st = 0; st < chain.nsteps; ++st) {
     const ChainStep s = chain.s[st];
     if (s.kind == 0) {
       for (int b = tid; b < s.nblk; b += blockDim.x) {
-        int i0 = s.idx[4 * b + 0], i1 = s.idx[4 * b + 1], i2 = s.idx[4 * b + 2], i3 = s.idx[4 * b + 3];
+        int i0, i1, i2, i3;
         cplx m[4][4];
-        const cplx* vp = s.val + 16 * (size_t)b;
+        if (b == tid) {
+          i0 = inx[0]; i1 = inx[1]; i2 = inx[2]; i3 = inx[3];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            cplx t = (s.mode == OP_N || s.mode == OP_J) ? vp[4 * r + c] : vp[4 * c + r];
-            if (s.mode == OP_C || s.mode == OP_J) t.y = -t.y;
-            m[r][c] = t;
-          }
+            for (int c = 0; c < 4; ++c) m[r][c] = mnx[r][c];
+          prefetch_block(st + 1);
+        } else {
+          i0 = s.idx[4 * b + 0]; i1 = s.idx[4 * b + 1]; i2 = s.idx[4 * b + 2]; i3 = s.idx[4 * b + 3];
+          const cplx* vp = s.val + 16 * (size_t)b;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              cplx t = (s.mode == OP_N || s.mode == OP_J) ? vp[4 * r + c] : vp[4 * c + r];
+              if (s.mode == OP_C || s.mode == OP_J) t.y = -t.y;
+              m[r][c] = t;
+            }
+        }
         for (int v = 0; v < nvec; ++v) {
           cplx* xv = x + (size_t)v * ldx;
           cplx a0 = xv[i0], a1 = xv[i1], a2 = xv[i2], a3 = xv[i3];
@@ -62,10 +100,12 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
           xv[i0] = y[0]; xv[i1] = y[1]; xv[i2] = y[2]; xv[i3] = y[3];
         }
       }
+      if (tid >= s.nblk) prefetch_block(st + 1);
       __syncthreads();
     } else {
       // interaction exponential of one time slice (interactions.jl:35-88):
       // C = cosh(lam*dtau*|phi|), S = (i phi2 - phi1) sign sinh/|phi|, R = -phi3 sign sinh/|phi|
+      prefetch_block(st + 1);
       for (int i = tid; i < nsites; i += blockDim.x) {
         const double* h = hsfield + 3 * ((size_t)i + (size_t)nsites * s.slice);
         double p1 = h[0], p2 = h[1], p3 = h[2];

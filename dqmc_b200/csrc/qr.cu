@@ -15,6 +15,9 @@ namespace cg = cooperative_groups;
 // The dots with the already-finished columns give V^H v_j, i.e. the compact-WY T factor, for free.
 // =====================================================================================================
 #define QR_LDA 33
+// cluster rank that accumulates the compact-WY T factor: rank 0 (which owns only the 32-row diagonal block) while the
+// other CTAs have long slabs, rank 1 once the slabs are short and rank 0 (masked inner loops, pushes row j) is the slowest
+__host__ __device__ __forceinline__ int panel_t_rank(int m) { return (m - QR_NB) >= (QR_CL - 1) * 48 ? 0 : 1; }
 #define QR_TX_BYTES ((QR_CL + 1) * QR_NB * 16)   // per column and CTA: QR_CL partial-dot vectors + row j
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +74,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
 #define PSTAMP(k) do { if (GENERAL && prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
   const int rank = (int)cl.block_rank();
   const int tid = threadIdx.x, g = tid >> 5, c = tid & 31;
+  const bool doT = (rank == panel_t_rank(m));     // the CTA that accumulates the compact-WY T factor
   cplx x[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -131,7 +135,8 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
       if (GENERAL) st_async_c16(r_row + par * (QR_NB * 16), S.rowl[c], r_bar + 8 * par);
     }
     PSTAMP(1);
-    if (GENERAL && j > 0 && g < 8) {
+#ifndef QRV_NOT
+    if (doT && j > 0 && g < 8) {
       // T(0:jp,jp) = -tau_jp * T(0:jp,0:jp) * g for the previous column jp = j-1 (zlarft, forward/columnwise) in the
       // shadow of the exchange: warp g owns rows i = g + 8q; lane = (q, h) sums k = h, h+8, ... and the 8 h-lanes combine
       const int jp = j - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
@@ -154,6 +159,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
       }
       __syncwarp();
     }
+#endif
     mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
     // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
     PSTAMP(2);
@@ -174,11 +180,18 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
     if (nrm2 == 0.0) {
       beta = 0.0; tau = cmake(0.0, 0.0); scale = cmake(0.0, 0.0);
     } else {
+#ifdef QRV_FAKEMATH
+      const double nrm = nrm2 * 0.5;
+      beta = alpha.x >= 0.0 ? -nrm : nrm;
+      const double id = 0.3 * (aa + nrm2 + 2.0 * fabs(alpha.x) * nrm);
+      const double ib = 0.3 * beta;
+#else
       const double nrm = sqrt(nrm2);
       beta = alpha.x >= 0.0 ? -nrm : nrm;
       // |alpha - beta|^2 = 2 |alpha|^2 + t_j + 2 |Re alpha| nrm: independent of the division that gives 1/beta
       const double id = 1.0 / (aa + nrm2 + 2.0 * fabs(alpha.x) * nrm);
       const double ib = 1.0 / beta;
+#endif
       const double ar = alpha.x - beta;
       tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
       scale = cmake(ar * id, -alpha.y * id);
@@ -187,7 +200,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
     cplx wc = rowc;
     cfma(wc, cconj(scale), tc);
     wc = cmul(cconj(tau), wc);
-    if (GENERAL && g < 8) {
+    if (doT && g < 8) {
       // g_c = V_c^H v_j = conj(V[j][c]) + scale * conj(t_c)   (c < j)
       cplx gg = cconj(rowc);
       cfma(gg, scale, cconj(tc));
@@ -221,7 +234,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
     PSTAMP(4);
   }
   if (GENERAL && prof && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
-  if (GENERAL && g < 8) {   // T column of the last reflector
+  if (doT && g < 8) {   // T column of the last reflector
     const int jp = nb - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
     cplx acc = cmake(0.0, 0.0);
     if (i < jp) {
@@ -251,7 +264,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
     const int rl = e % nloc, cc = e / nloc;
     A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
   }
-  if (GENERAL) {
+  if (doT) {
     for (int e = tid; e < QR_NB * QR_NB; e += NW * 32) {
       int i = e % QR_NB, k = e / QR_NB;
       Tout[e] = (i < nb && k < nb) ? S.Tsm[i][k] : cmake(0.0, 0.0);
@@ -284,7 +297,7 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     const int rl = e % nloc, cc = e / nloc;
     a[rl * QR_LDA + cc] = cc < nb ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
   }
-  if (rank == 0)
+  if (rank == panel_t_rank(m))
     for (int e = tid; e < QR_NB * (QR_NB + 1); e += NW * 32) (&S.Tsm[0][0])[e] = cmake(0.0, 0.0);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[0])));
