@@ -30,6 +30,15 @@ CONFIGS = {
 MODEL = dict(hoppings="1.0,0.5,-0.5,-1.0", mu=-0.5, lam=0.5, r=2.0, c=3.0, u=1.0, delta_tau=0.1, box=0.5)
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -288,13 +297,17 @@ def run_ours(args, cfg, rank, world, local_rank):
         if dom_map[dom] is not None:
             rf = dict(kr[dom_map[dom]])
             roof = {"kernel": dom_map[dom], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": rf["unit"],
-                    "frac": rf["frac"], "traffic": None, "peak_source": rf["peak_source"]}
+                    "frac": rf["frac"], "traffic": ncu_traffic({"wrap": "apply_chain_kernel", "udt": "qr_panel_kernel",
+                                                                   "calculate_greens": "larfb_kernel"}[dom_map[dom]]),
+                    "peak_source": rf["peak_source"]}
         else:
             # local updates: FP64 work = rank-4 Woodbury updates (32 n^2 flops per accepted proposal, flushed as GEMMs)
             t_lu = phases["local_updates"] * 1e-3
             ach = acc_rate * M * N * 32.0 * n * n / t_lu / 1e12
             roof = {"kernel": "local_updates_kernel", "bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
-                    "frac": ach / f64_peak, "traffic": None, "peak_source": "cuBLAS ZGEMM measured in this run",
+                    "frac": ach / f64_peak, "traffic": ncu_traffic("local_updates_kernel"),
+                    "traffic_note": "DRAM bytes per launch (one time slice) from ncu; algorithmic flops per launch = accepted x 32 n^2",
+                    "peak_source": "cuBLAS ZGEMM measured in this run",
                     "serial_floor_us_per_proposal": kr["local_updates_slice"]["us_per_proposal"]}
         t_cpu, acc_cpu = cpu_block_sample(cfg, 1)
         line = {"metric": "sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
