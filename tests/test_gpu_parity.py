@@ -176,9 +176,10 @@ def test_local_updates_golden(golden_o3):
     mc.close()
 
 
-@pytest.mark.parametrize("L,M,delay", [(4, 20, 0), (4, 20, 3), (8, 20, 0)])
+@pytest.mark.parametrize("L,M,delay", [(4, 20, 0), (4, 20, 3), (8, 20, 0), (4, 50, 0), (8, 200, 0)])
 def test_sweep_vs_oracle_shared_stream(L, M, delay):
     # same field + same uniform stream => identical accept/reject sequence, bit-exact field, G within 1e-10
+    # ((4, 50) and (8, 200) are BASELINE.json configs[0] and configs[1]: a full up-down sweep each)
     from dqmc_b200 import UniformStream
     mc, om = _mk(L, M, False, delay=delay)
     rs = np.random.RandomState(5)
