@@ -135,7 +135,7 @@ def run_reference(args, cfg, rank, world):
                              "sample": "each step = 1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) "
                                        "at the workload's L on a 4-block chain, scaled to a full sweep" % (cfg["slices"] // cfg["safe_mult"])},
             "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -329,7 +329,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                            % (M // sm, L), "acceptance": acc_cpu},
                 "checks": {"max_propagation_error": err, "nonreal_detratios": nonreal,
                            "pooled_phi2_mean": float(pooled_mean[0]), "pooled_phi2_var": float(pooled_var[0])}}
-        print(json.dumps(line))
+        emit(line)
     mc.close()
     if world > 1:
         torch.distributed.barrier()
@@ -340,7 +340,24 @@ def mc_delay(args):
     return args.delay if args.delay > 0 else 16
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints meanwhile (NCCL's
+    version banner, warnings) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                   # file-descriptor level: also catches C libraries (NCCL banner)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
