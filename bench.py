@@ -275,6 +275,27 @@ def run_ours(args, cfg, rank, world, local_rank):
                "ms_per_sweep_per_chain": wall2 / args.steps * 1e3}
         mc2.close()
 
+    # ---- extra: the same sweep with the magnetic flux on (complex Peierls-phase plaquette factors; all O(3) test XMLs of the
+    # reference use it, the README's speed test had it off -> headline off, this series on)
+    bfield = None
+    if args.bfield_series:
+        pb = Params(L=L, slices=M, safe_mult=sm, delta_tau=MODEL["delta_tau"], lambda_=MODEL["lam"], r=MODEL["r"], c=MODEL["c"],
+                    u=MODEL["u"], mu1=MODEL["mu"], mu2=MODEL["mu"], hoppings=MODEL["hoppings"], box=MODEL["box"],
+                    Bfield=True, all_checks=bool(args.all_checks))
+        mcb = DQMC(pb, device=local_rank, delay=args.delay)
+        mcb.init(field)
+        mcb.set_uniforms(u)
+        mcb.sweep(None)
+        mcb.set_timing(True); mcb.timers()
+        for _ in range(args.steps):
+            mcb.sweep(None)
+        mcb.sync()
+        tb = mcb.timers()["sweep"] * 1e-3
+        errb, _nr = mcb.checks()
+        bfield = {"value": args.steps / tb, "unit": "sweeps/s (this rank's chain)", "ms_per_sweep": tb / args.steps * 1e3,
+                  "max_propagation_error": errb}
+        mcb.close()
+
     # ---- pooled measurement bins across chains (the path's only collective; outside the timed region)
     h = mc.hsfield
     phi2 = np.einsum("kis,kis->is", h, h).ravel()
@@ -322,7 +343,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "roofline": roof,
                 "sweep_roofline": {"flops": f_sweep, "bytes": b_sweep, "t_roofline_ms": t_roof * 1e3, "frac": t_roof / (t_dev / args.steps),
                                    "fp64_peak_tflops": f64_peak, "hbm_gbs": hbm_gbs},
-                "phases_ms_per_sweep": phases, "kernels": kr, "two_chains_per_gpu": two,
+                "phases_ms_per_sweep": phases, "kernels": kr, "two_chains_per_gpu": two, "bfield_on": bfield,
                 "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
                                  "sample": "1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) at L=%d on a "
                                            "4-block chain, scaled to a full sweep; oracle port, NumPy/SciPy + OpenBLAS, all host cores"
@@ -366,6 +387,7 @@ def main():
     ap.add_argument("--config", default="L16_beta40", choices=sorted(CONFIGS))
     ap.add_argument("--delay", type=int, default=0)
     ap.add_argument("--all-checks", type=int, default=1)
+    ap.add_argument("--bfield-series", type=int, default=1, help="also time the sweep with the magnetic flux on (extra)")
     ap.add_argument("--two-chains", type=int, default=1, help="also time two chains per GPU (extra, not the headline)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
