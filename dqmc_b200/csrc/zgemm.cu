@@ -1,21 +1,27 @@
 #include "zgemm.cuh"
 
+#ifndef ZGEMM_KT
+#define ZGEMM_KT 16   // k-tile of the large-tile variants (two shared-memory stages)
+#endif
+
 // Operand tiles live in shared memory in *fragment order*: for every (k-step of 4, tile of 8 rows/cols)
 // the 32 lanes' elements are contiguous, element `lane` being X[o = lane/4][k = lane%4] as (re,im).
 // A fragment load is then one conflict-free LDS.128 per lane, and the global->shared copy reads
 // 128 B (op N on A / op T,C on B) or 64 B (the other cases) contiguous segments.
 //
 // One complex 8x8x4 tile product = 4 real DMMAs:  Cr += Ar*Br - Ai*Bi,  Ci += Ar*Bi + Ai*Br.
-template <int WTM, int WTN, int NWM, int NWN>
+template <int WTM, int WTN, int NWM, int NWN, int KT>
 __global__ void __launch_bounds__(NWM * NWN * 32)
 zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int lda, int opA,
              const cplx* __restrict__ B, int ldb, int opB, cplx beta, cplx* __restrict__ C, int ldc) {
-  constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8, KT = 8, KS = KT / 4;
+  constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8, KS = KT / 4;
   constexpr int NW = NWM * NWN;
   constexpr int FA = (BM / 8) * KS, FB = (BN / 8) * KS;       // fragments per stage
   constexpr int LA = (FA + NW - 1) / NW, LB = (FB + NW - 1) / NW;
-  __shared__ __align__(16) cplx As[FA * 32];
-  __shared__ __align__(16) cplx Bs[FB * 32];
+  // two stages: the next k-tile is written while the current one is read, one barrier per k-tile
+  extern __shared__ __align__(16) unsigned char zsm[];
+  cplx* As = reinterpret_cast<cplx*>(zsm);                    // [2][FA*32]
+  cplx* Bs = As + 2 * FA * 32;                                // [2][FB*32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp % NWM, wn = warp / NWM;
@@ -59,23 +65,29 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
       rb[t] = v;
     }
   };
+  auto sstore = [&](int stage) {
+#pragma unroll
+    for (int t = 0; t < LA; ++t) { int f = warp + t * NW; if (f < FA) As[(stage * FA + f) * 32 + lane] = ra[t]; }
+#pragma unroll
+    for (int t = 0; t < LB; ++t) { int f = warp + t * NW; if (f < FB) Bs[(stage * FB + f) * 32 + lane] = rb[t]; }
+  };
 
   gload(0);
+  sstore(0);
+  __syncthreads();
+  int stage = 0;
   for (int k0 = 0; k0 < K; k0 += KT) {
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < LA; ++t) { int f = warp + t * NW; if (f < FA) As[f * 32 + lane] = ra[t]; }
-#pragma unroll
-    for (int t = 0; t < LB; ++t) { int f = warp + t * NW; if (f < FB) Bs[f * 32 + lane] = rb[t]; }
-    __syncthreads();
-    if (k0 + KT < K) gload(k0 + KT);
+    const bool more = k0 + KT < K;
+    if (more) gload(k0 + KT);
+    const cplx* as = As + stage * FA * 32;
+    const cplx* bs = Bs + stage * FB * 32;
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk) {
       cplx a[WTM], b[WTN];
 #pragma unroll
-      for (int i = 0; i < WTM; ++i) a[i] = As[(kk * (BM / 8) + wm * WTM + i) * 32 + lane];
+      for (int i = 0; i < WTM; ++i) a[i] = as[(kk * (BM / 8) + wm * WTM + i) * 32 + lane];
 #pragma unroll
-      for (int j = 0; j < WTN; ++j) b[j] = Bs[(kk * (BN / 8) + wn * WTN + j) * 32 + lane];
+      for (int j = 0; j < WTN; ++j) b[j] = bs[(kk * (BN / 8) + wn * WTN + j) * 32 + lane];
 #pragma unroll
       for (int i = 0; i < WTM; ++i)
 #pragma unroll
@@ -86,6 +98,9 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
           dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
         }
     }
+    if (more) sstore(stage ^ 1);   // the other stage was last read before the previous barrier
+    __syncthreads();
+    stage ^= 1;
   }
 
   const bool use_c = (beta.x != 0.0 || beta.y != 0.0);
@@ -106,22 +121,32 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
       }
 }
 
+template <int WTM, int WTN, int NWM, int NWN, int KT>
+static int zgemm_launch(cudaStream_t stream, int opA, int opB, int M, int N, int K, cplx alpha, const cplx* A, int lda,
+                        const cplx* B, int ldb, cplx beta, cplx* C, int ldc) {
+  constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8;
+  constexpr size_t smem = sizeof(cplx) * 2 * 32 * ((BM / 8) * (KT / 4) + (BN / 8) * (KT / 4));
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(zgemm_kernel<WTM, WTN, NWM, NWN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN);
+  zgemm_kernel<WTM, WTN, NWM, NWN, KT><<<g, NWM * NWN * 32, smem, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
+  return 0;
+}
+
 int zgemm(cudaStream_t stream, int opA, int opB, int M, int N, int K, cplx alpha, const cplx* A, int lda,
           const cplx* B, int ldb, cplx beta, cplx* C, int ldc, int num_sms) {
   if (M <= 0 || N <= 0) return 0;
   if (opA == OP_J || opB == OP_J) { snprintf(g_errbuf, sizeof(g_errbuf), "zgemm: OP_J unsupported"); return -1; }
   auto tiles = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
   const long want = (long)num_sms * 3 / 4;
-  if (tiles(128, 64) >= want) {
-    dim3 g((M + 127) / 128, (N + 63) / 64);
-    zgemm_kernel<4, 4, 4, 2><<<g, 256, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
-  } else if (tiles(64, 64) >= want) {
-    dim3 g((M + 63) / 64, (N + 63) / 64);
-    zgemm_kernel<4, 2, 2, 4><<<g, 256, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
-  } else {
-    dim3 g((M + 31) / 32, (N + 31) / 32);
-    zgemm_kernel<2, 2, 2, 2><<<g, 128, 0, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
-  }
+  int rc;
+  if (tiles(128, 64) >= want) rc = zgemm_launch<4, 4, 4, 2, ZGEMM_KT>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (tiles(64, 64) >= want) rc = zgemm_launch<4, 2, 2, 4, ZGEMM_KT>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else rc = zgemm_launch<2, 2, 2, 2, 8>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
