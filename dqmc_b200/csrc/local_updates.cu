@@ -73,6 +73,13 @@ __device__ __forceinline__ cplx det3(cplx a, cplx b, cplx c, cplx d, cplx e, cpl
   return cadd(csub(cmul(a, t1), cmul(b, t2)), cmul(c, t3));
 }
 
+// rare path (|x| > 1), kept out of line so that it does not sit in the instruction stream of the site loop
+__device__ __noinline__ void cosh_sinhc_large(double z, double* ch, double* shc) {
+  const double x = sqrt(z), em1 = expm1(x), q = em1 / (em1 + 1.0);
+  *ch = 1.0 + 0.5 * em1 * q;
+  *shc = 0.5 * (em1 + q) / x;
+}
+
 // cosh(x) and sinh(x)/x as functions of z = x^2 (Taylor series, |x| <= 1: truncation < 1e-18), so that neither a square
 // root nor a division by |phi| is needed; larger arguments fall back to expm1.
 __device__ __forceinline__ void cosh_sinhc(double z, double* ch, double* shc) {
@@ -90,9 +97,7 @@ __device__ __forceinline__ void cosh_sinhc(double z, double* ch, double* shc) {
     *ch = fma(c, z, 1.0);
     *shc = fma(s, z, 1.0);
   } else {
-    const double x = sqrt(z), em1 = expm1(x), q = em1 / (em1 + 1.0);
-    *ch = 1.0 + 0.5 * em1 * q;
-    *shc = 0.5 * (em1 + q) / x;
+    cosh_sinhc_large(z, ch, shc);
   }
 }
 
@@ -329,9 +334,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         const int w8 = (tp >> 2) & 1, k8 = tp & 3, p8 = tp >> 3;
         const cplx* sbase = (w8 ? Bmb : Atb) + (size_t)(i + 1 + k8 * N) * ldk;
         cplx* dbase = (w8 ? Bs4 : As4) + (nb * 4 + k8) * lds;
-        unsigned long long vx[8], vy[8];
+        unsigned long long vx[4], vy[4];   // np <= 64 (kmax <= 16): four window columns per thread
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 4; ++u)
           if (have_next && p8 + 16 * u < np)
             asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
         if (have_next) {   // G values: into shared memory while the A/B loads are in flight
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 4; ++u)
           if (have_next && p8 + 16 * u < np) {
             while (vx[u] == LU_SENT || vy[u] == LU_SENT)
               asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx[u]), "=l"(vy[u]) : "l"(sbase + p8 + 16 * u) : "memory");
@@ -362,8 +367,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
         else { pa = As4 + (b * 4 + (idx >> 2)) * lds; pb = Bs4 + (nb * 4 + (idx & 3)) * lds; base = Gx2[idx]; }
         cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
         int p = h;
+#pragma unroll 1
         for (; p + 2 < np; p += 4) { cfma(acc0, pa[p], pb[p]); cfma(acc1, pa[p + 2], pb[p + 2]); }
-        for (; p < np; p += 2) cfma(acc0, pa[p], pb[p]);
+        if (p < np) cfma(acc0, pa[p], pb[p]);
         cplx acc = cadd(acc0, acc1);
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
@@ -389,8 +395,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           const cplx* own = (isB ? Bown : Aown) + (size_t)rl * lds;
           const cplx* site = (isB ? As4 : Bs4) + (b * 4 + kq) * lds;
           int p = h;
+#pragma unroll 1
           for (; p + 2 < np; p += 4) { cfma(acc0, own[p], site[p]); cfma(acc1, own[p + 2], site[p + 2]); }
-          for (; p < np; p += 2) cfma(acc0, own[p], site[p]);
+          if (p < np) cfma(acc0, own[p], site[p]);
         }
         cplx acc = cadd(acc0, acc1);
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
