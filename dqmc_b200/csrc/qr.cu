@@ -363,22 +363,17 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
       }
   };
   {
-    // all CTAs stream the same V: each one starts at a different step of its chunk (rotation) so that the CTAs, which run in
-    // lock step, do not all ask the L2 for the same lines at the same moment
     cplx avA[2][4], bvA[2], avB[2][4], bvB[2];
-    const int nst = (max(kend - kbeg, 0) + 7) / 8;
-    const int rot1 = nst > 0 ? (int)((blockIdx.x * 3u) % (unsigned)nst) : 0;
-    auto r0_of = [&](int s) { int q = s + rot1; if (q >= nst) q -= nst; return kbeg + 8 * q; };
-    int s = 0;
-    if (s < nst) load_step(r0_of(s), avA, bvA);
-    while (s < nst) {
-      if (s + 1 < nst) load_step(r0_of(s + 1), avB, bvB);
+    int r0 = kbeg;
+    if (r0 < kend) load_step(r0, avA, bvA);
+    while (r0 < kend) {
+      if (r0 + 8 < kend) load_step(r0 + 8, avB, bvB);
       mma_step(avA, bvA);
-      ++s;
-      if (s >= nst) break;
-      if (s + 1 < nst) load_step(r0_of(s + 1), avA, bvA);
+      r0 += 8;
+      if (r0 >= kend) break;
+      if (r0 + 8 < kend) load_step(r0 + 8, avA, bvA);
       mma_step(avB, bvB);
-      ++s;
+      r0 += 8;
     }
   }
   if (warp >= 4) {
@@ -449,18 +444,16 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
   };
   {
     cplx avA[8], cvA[2], avB[8], cvB[2];
-    const int rot3 = (int)((blockIdx.x * 7u) % (unsigned)max(ntile, 1));
-    auto rt_of = [&](int q) { int t = q + rot3; if (t >= ntile) t -= ntile; return t; };
-    int q = warp;
-    if (q < ntile) load_tile(rt_of(q), avA, cvA);
-    while (q < ntile) {
-      if (q + 8 < ntile) load_tile(rt_of(q + 8), avB, cvB);
-      do_tile(rt_of(q), avA, cvA);
-      q += 8;
-      if (q >= ntile) break;
-      if (q + 8 < ntile) load_tile(rt_of(q + 8), avA, cvA);
-      do_tile(rt_of(q), avB, cvB);
-      q += 8;
+    int rt = warp;
+    if (rt < ntile) load_tile(rt, avA, cvA);
+    while (rt < ntile) {
+      if (rt + 8 < ntile) load_tile(rt + 8, avB, cvB);
+      do_tile(rt, avA, cvA);
+      rt += 8;
+      if (rt >= ntile) break;
+      if (rt + 8 < ntile) load_tile(rt + 8, avA, cvA);
+      do_tile(rt, avB, cvB);
+      rt += 8;
     }
   }
 }
@@ -773,11 +766,7 @@ trsm_kernel(const cplx* __restrict__ A, int lda, int n, cplx* __restrict__ Y, in
     }
     // y[0:j0] -= R[0:j0, block kb] x
     const int ntile = j0 / 8;
-    // every CTA needs the same tiles of R: visiting them in a CTA-dependent rotation keeps the CTAs (which run in lock step)
-    // from hammering the same L2 lines at the same time
-    const int rot = (int)((blockIdx.x * 5u) % (unsigned)max(ntile, 1));
-    for (int q = warp; q < ntile; q += 8) {
-      const int rt = (q + rot) % ntile;
+    for (int rt = warp; rt < ntile; rt += 8) {
       const int r = rt * 8 + lo;
       cplx av[8];
 #pragma unroll
