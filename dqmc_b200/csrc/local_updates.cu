@@ -181,6 +181,9 @@ __device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, const
   }
 }
 
+// PROF = true adds the cycle counters of tools/lu_profile.py; the production instantiation carries none of that code (the site
+// loop's instruction stream is as large as the instruction cache, every instruction less counts).
+template <bool PROF>
 __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.n, N = a.nsites, ldk = 4 * a.kmax, rpc = a.rpc;
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0;
   // optional cycle profile of CTA 0: arrival stamps before the two CTA barriers of an iteration (a clock read right
   // after bar.sync would capture the barrier's issue, not its release)
-  const bool prof = (a.prof != nullptr) && blockIdx.x == 0;
+  const bool prof = PROF && (a.prof != nullptr) && blockIdx.x == 0;
   __shared__ long long stampA[8], stampB[8], stampP[8];
   __shared__ long long p_role[8], p_role1[8];
   if (tid < 8) { p_role[tid] = 0; p_role1[tid] = 0; }
@@ -632,12 +635,13 @@ size_t local_updates_smem(const LUArgs& a) {
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid) {
   const size_t smem = local_updates_smem(a);
   static size_t smem_lim = 0;
-  if (smem_lim == 0 && set_max_dynamic_smem(local_updates_kernel, &smem_lim)) return -1;
+  if (smem_lim == 0 && (set_max_dynamic_smem(local_updates_kernel<false>, &smem_lim) || set_max_dynamic_smem(local_updates_kernel<true>, &smem_lim))) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "local_updates: shared memory %zu > %zu", smem, smem_lim); return -1; }
   if (a.rpc > 64) { snprintf(g_errbuf, sizeof(g_errbuf), "local_updates: rows per CTA %d > 64", a.rpc); return -1; }
   LUArgs args = a;
   void* params[] = {&args};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)local_updates_kernel, dim3(grid), dim3(256), params, smem, st));
+  const void* kern = a.prof ? (const void*)local_updates_kernel<true> : (const void*)local_updates_kernel<false>;
+  CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), params, smem, st));
   g_launches++;
   return 0;
 }
