@@ -66,12 +66,12 @@ struct PanelSmem {
 // block: rows at or above the diagonal are masked, row j is pushed to the cluster, the T factor is accumulated);
 // GENERAL = false are the CTAs below, whose inner loops are bare multiply-adds.  A finished column c stays UNSCALED in
 // registers (v = sc_c * x below the diagonal); the factor is applied to its dot products and at the final store.
-template <int NW, int T, bool GENERAL>
+template <int NW, int T, bool GENERAL, bool PROF>
 __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
                                            int m, int nb, int r_begin, int nloc, cplx* __restrict__ tau_out,
                                            double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
   long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define PSTAMP(k) do { if (GENERAL && prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
+#define PSTAMP(k) do { if (PROF && GENERAL && prof) { long long t_ = clock64(); pc[k] += t_ - tprev; tprev = t_; } } while (0)
   const int rank = (int)cl.block_rank();
   const int tid = threadIdx.x, g = tid >> 5, c = tid & 31;
   const bool doT = (rank == panel_t_rank(m));     // the CTA that accumulates the compact-WY T factor
@@ -233,7 +233,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
     }
     PSTAMP(4);
   }
-  if (GENERAL && prof && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
+  if (PROF && GENERAL && prof && tid == 0) { for (int q = 0; q < 5; ++q) prof[q] += pc[q]; prof[5] += nb; }
   if (doT && g < 8) {   // T column of the last reflector
     const int jp = nb - 1, q = c >> 3, h = c & 7, i = g + 8 * q;
     cplx acc = cmake(0.0, 0.0);
@@ -277,7 +277,7 @@ __device__ __forceinline__ void panel_body(PanelSmem<NW>& S, cplx* a, cg::cluste
 // Row split: rank 0 owns rows [0, QR_NB) (or all m of them if fewer), the rest is dealt evenly to ranks 1..QR_CL-1.
 __host__ __device__ __forceinline__ int panel_rows_below(int m) { return (max(0, m - QR_NB) + QR_CL - 2) / (QR_CL - 1); }
 
-template <int NW, int T>
+template <int NW, int T, bool PROF>
 __global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(NW * 32)
 qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__ tau_out,
                 double* __restrict__ dabs_out, cplx* __restrict__ Tout, long long* __restrict__ prof) {
@@ -305,8 +305,8 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (rank == 0) panel_body<NW, QR_NB / NW, true>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
-  else panel_body<NW, T, false>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
+  if (rank == 0) panel_body<NW, QR_NB / NW, true, PROF>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
+  else panel_body<NW, T, false, PROF>(S, a, cl, A, lda, m, nb, r_begin, nloc, tau_out, dabs_out, Tout, prof);
 }
 
 // =====================================================================================================
@@ -597,9 +597,10 @@ long long* g_qr_prof = nullptr;
 template <int NW, int T>
 static int launch_panel_t(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* Tf, size_t smem) {
   static size_t smem_lim = 0;
-  if (smem_lim == 0 && set_max_dynamic_smem(qr_panel_kernel<NW, T>, &smem_lim)) return -1;
+  if (smem_lim == 0 && (set_max_dynamic_smem(qr_panel_kernel<NW, T, false>, &smem_lim) || set_max_dynamic_smem(qr_panel_kernel<NW, T, true>, &smem_lim))) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
-  qr_panel_kernel<NW, T><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, g_qr_prof);
+  if (g_qr_prof) qr_panel_kernel<NW, T, true><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, g_qr_prof);
+  else qr_panel_kernel<NW, T, false><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, nullptr);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
