@@ -116,6 +116,16 @@ def cpu_block_sample(cfg, nblocks=1):
     return dt / nblocks * blocks_per_sweep, acc / (nblocks * sm)
 
 
+def cpu_one_thread(cfg):
+    """The same sample at ONE BLAS thread (the reference's default: app/dqmc.jl:33-37 sets BLAS threads to 1)."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None
+    with threadpool_limits(limits=1):
+        return cpu_block_sample(cfg, 1)[0]
+
+
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
@@ -331,6 +341,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                     "peak_source": "cuBLAS ZGEMM measured in this run",
                     "serial_floor_us_per_proposal": kr["local_updates_slice"]["us_per_proposal"]}
         t_cpu, acc_cpu = cpu_block_sample(cfg, 1)
+        t_cpu1 = cpu_one_thread(cfg)
         line = {"metric": "sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
@@ -347,7 +358,10 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
                                  "sample": "1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) at L=%d on a "
                                            "4-block chain, scaled to a full sweep; oracle port, NumPy/SciPy + OpenBLAS, all host cores"
-                                           % (M // sm, L), "acceptance": acc_cpu},
+                                           % (M // sm, L), "acceptance": acc_cpu,
+                                 "one_blas_thread": {"value": 1.0 / t_cpu1 if t_cpu1 else None, "unit": "sweeps/s", "cores": 1,
+                                                     "note": "same sample at 1 BLAS thread, the reference driver's default "
+                                                             "(app/dqmc.jl:33-37)"}},
                 "checks": {"max_propagation_error": err, "nonreal_detratios": nonreal,
                            "pooled_phi2_mean": float(pooled_mean[0]), "pooled_phi2_var": float(pooled_var[0])}}
         emit(line)
