@@ -78,6 +78,7 @@ struct dqmc_ctx {
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
   int lu_grid, lu_rpc;
+  int lu_bar_mode, lu_bar_parity;   // grid barrier of the local-update kernel: 1 = monotonic counters alternating per launch
   bool timing;
   std::vector<TimerRec> trecs;
   std::vector<cudaEvent_t> evpool;
@@ -175,6 +176,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   CU(c, cudaEventCreateWithFlags(&c->qra.eA, cudaEventDisableTiming));
   CU(c, cudaEventCreateWithFlags(&c->qra.eB, cudaEventDisableTiming));
   c->lookahead = getenv("DQMC_NO_LOOKAHEAD") == nullptr;
+  { const char* e = getenv("DQMC_LU_BAR"); c->lu_bar_mode = e ? atoi(e) : 1; c->lu_bar_parity = 0; }
   const size_t n = c->n, nn = n * n;
   TRY(c, dmalloc(c, &c->G, nn));
   TRY(c, dmalloc(c, &c->Gtmp, nn));
@@ -781,6 +783,7 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   a.G = c->G; a.At = c->At; a.Bm = c->Bm; a.hs = c->hs; a.nbr = c->nbr;
   a.unif = c->unif; a.nunif = c->unif_n; a.pos = c->d_pos; a.accepted = c->d_acc; a.dS = c->d_dS;
   a.flags = c->d_flags; a.bar = c->d_bar; a.prof = c->lu_prof ? c->d_prof : nullptr;
+  a.bar_mode = c->lu_bar_mode; a.bar_parity = c->lu_bar_parity; c->lu_bar_parity ^= 1;
   TRY(c, launch_local_updates(c->st, a, c->lu_grid));
   return 0;
 }

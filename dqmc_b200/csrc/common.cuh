@@ -97,3 +97,20 @@ DQMC_D void grid_barrier(unsigned int* bar, unsigned int nblocks) {
   }
   __syncthreads();
 }
+
+// Same, with a monotonic arrival counter and no generation word: CTA k-th barrier of a launch waits for the counter to reach
+// k * nblocks, so the release is the last arrival's atomic itself (one L2 round trip less than the count + generation scheme).
+// The counter must be zero at launch (the local-update kernel alternates between two counters and clears the idle one).
+DQMC_D void grid_barrier_mono(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}

@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     uw[e] = e < navail ? a.unif[pos0 + e] : 0.0;
   }
   if (tid == 0) s_exh = 0;
+  unsigned int* const bar_ctr = a.bar + 2 + a.bar_parity;   // monotonic barrier counter of this launch (zero at launch)
+  unsigned int bar_target = 0;
+  if (a.bar_mode && blockIdx.x == 0 && tid == 0) a.bar[2 + (1 - a.bar_parity)] = 0;   // the next launch's counter
   int off = 0;                                              // stream position relative to pos0
   long long nacc = 0;
   double dS_sum = 0.0;
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
     if (do_flush) {
       n_fl++;
       long long tf0 = clock64();
-      grid_barrier(a.bar, gridDim.x);
+      if (a.bar_mode) { bar_target += gridDim.x; grid_barrier_mono(bar_ctr, bar_target); } else grid_barrier(a.bar, gridDim.x);
       long long tf1 = clock64();
       const int K = 4 * kc;
       const int lo = lane >> 2, lk = lane & 3;
@@ -513,21 +516,15 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        cplx gv[4][2][2];
+        // 3M complex product: S1 = Ar Br, S2 = Ai Bi, S3 = (Ar + Ai)(Br + Bi);  Re = S1 - S2,  Im = S3 - S1 - S2
+        // (three real DMMAs per complex tile product instead of four; the flush is DMMA-bound)
+        double s1[4][2][2], s2[4][2][2], s3[4][2][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
           for (int y = 0; y < 2; ++y)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
-              gv[x][y][e] = (row < n && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
-            }
-        double cr[4][2][2], ci[4][2][2];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 2; ++y) cr[x][y][0] = cr[x][y][1] = ci[x][y][0] = ci[x][y][1] = 0.0;
+            for (int e = 0; e < 2; ++e) s1[x][y][e] = s2[x][y][e] = s3[x][y][e] = 0.0;
         for (int ch = 0; ch < nch; ++ch) {
           if (ch + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
           else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -542,17 +539,34 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 #pragma unroll
             for (int y = 0; y < 2; ++y) bv[y] = fb[(wn * 16 + y * 8 + lo) * 36 + ks * 4 + lk];
 #pragma unroll
+            double asum[4], bsum[2];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) asum[x] = av[x].x + av[x].y;
+#pragma unroll
+            for (int y = 0; y < 2; ++y) bsum[y] = bv[y].x + bv[y].y;
+#pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
               for (int y = 0; y < 2; ++y) {
-                dmma884(cr[x][y][0], cr[x][y][1], av[x].x, bv[y].x);
-                dmma884(cr[x][y][0], cr[x][y][1], -av[x].y, bv[y].y);
-                dmma884(ci[x][y][0], ci[x][y][1], av[x].x, bv[y].y);
-                dmma884(ci[x][y][0], ci[x][y][1], av[x].y, bv[y].x);
+                dmma884(s1[x][y][0], s1[x][y][1], av[x].x, bv[y].x);
+                dmma884(s2[x][y][0], s2[x][y][1], av[x].y, bv[y].y);
+                dmma884(s3[x][y][0], s3[x][y][1], asum[x], bsum[y]);
               }
           }
         }
         __syncthreads();                                   // staging buffers free for the next tile's loads
+        // G tile: read late (the accumulators of the 3M product leave no room to hold it during the DMMAs), all loads in flight
+        // before the first add
+        cplx gv[4][2][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
+              gv[x][y][e] = (row < n && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
+            }
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -561,11 +575,12 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
             for (int e = 0; e < 2; ++e) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
               if (row < n && col < n)
-                a.G[(size_t)col * n + row] = cmake(gv[x][y][e].x + cr[x][y][e], gv[x][y][e].y + ci[x][y][e]);
+                a.G[(size_t)col * n + row] = cmake(gv[x][y][e].x + (s1[x][y][e] - s2[x][y][e]),
+                                                   gv[x][y][e].y + (s3[x][y][e] - s1[x][y][e] - s2[x][y][e]));
             }
       }
       long long tf2 = clock64();
-      grid_barrier(a.bar, gridDim.x);
+      if (a.bar_mode) { bar_target += gridDim.x; grid_barrier_mono(bar_ctr, bar_target); } else grid_barrier(a.bar, gridDim.x);
       long long tf3 = clock64();
       if (prof && tid == 0) { pf[0] += tf1 - tf0; pf[1] += tf2 - tf1; pf[2] += tf3 - tf2; }
       {   // re-arm my rows of the buffer just consumed (nobody reads it again before the flush after next)

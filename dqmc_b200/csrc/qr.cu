@@ -1,4 +1,6 @@
 #include "qr.cuh"
+#include "zgemm.cuh"
+#include <cstdlib>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -805,20 +807,51 @@ trsm_kernel(const cplx* __restrict__ A, int lda, int n, cplx* __restrict__ Y, in
       }
 }
 
-int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
-               const double* rowscale, int num_sms) {
-  (void)num_sms;
-  const int nblk = (n + QR_NB - 1) / QR_NB;
-  trtri_diag_kernel<<<nblk, 32, 0, st>>>(A, lda, n, work);
-  CUDA_TRY(cudaGetLastError());
-  g_launches++;
+__global__ void row_scale_kernel(cplx* __restrict__ Y, int ldy, int n, int nrhs, const double* __restrict__ rowscale) {
+  const size_t total = (size_t)n * nrhs;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e % n), c = (int)(e / n);
+    cplx* p = Y + (size_t)c * ldy + r;
+    *p = cscale(*p, rowscale[r]);
+  }
+}
+
+static int trsm_block(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, const cplx* inv,
+                      const double* rowscale) {
   const int n8 = (n + 7) / 8 * 8, lds = n8 + 4;
   const size_t smem = sizeof(cplx) * ((size_t)8 * lds + QR_NB * 8 + QR_NB * QR_NB);
   static size_t smem_lim = 0;
   if (smem_lim == 0 && set_max_dynamic_smem(trsm_kernel, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "trsm: n=%d too large", n); return -1; }
-  trsm_kernel<<<(nrhs + 7) / 8, 256, smem, st>>>(A, lda, n, Y, ldy, nrhs, work, rowscale);
+  trsm_kernel<<<(nrhs + 7) / 8, 256, smem, st>>>(A, lda, n, Y, ldy, nrhs, inv, rowscale);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
+  return 0;
+}
+
+// Y <- R^-1 Y (optionally with the rows of the result scaled).  Above TRSM_BS rows the back substitution is blocked at the
+// host level: the per-CTA kernel (which streams its whole triangle from L2 for every 8 right-hand sides) solves TRSM_BS-row
+// diagonal blocks, the rectangular part of R goes through ZGEMM.
+#define TRSM_BS 512
+int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
+               const double* rowscale, int num_sms) {
+  const int nblk = (n + QR_NB - 1) / QR_NB;
+  trtri_diag_kernel<<<nblk, 32, 0, st>>>(A, lda, n, work);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  static const bool split = getenv("DQMC_TRSM_NOSPLIT") == nullptr;
+  if (n <= TRSM_BS || !split) return trsm_block(st, A, lda, n, Y, ldy, nrhs, work, rowscale);
+  const cplx one = cmake(1.0, 0.0), mone = cmake(-1.0, 0.0);
+  for (int j0 = (n - 1) / TRSM_BS * TRSM_BS; j0 >= 0; j0 -= TRSM_BS) {
+    const int len = min(TRSM_BS, n - j0);
+    if (trsm_block(st, A + (size_t)j0 * lda + j0, lda, len, Y + j0, ldy, nrhs, work + (size_t)(j0 / QR_NB) * QR_NB * QR_NB, nullptr))
+      return -1;
+    if (j0 > 0 && zgemm(st, OP_N, OP_N, j0, nrhs, len, mone, A + (size_t)j0 * lda, lda, Y + j0, ldy, one, Y, ldy, num_sms)) return -1;
+  }
+  if (rowscale) {
+    row_scale_kernel<<<num_sms * 4, 256, 0, st>>>(Y, ldy, n, nrhs, rowscale);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+  }
   return 0;
 }

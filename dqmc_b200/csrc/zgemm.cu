@@ -1,4 +1,5 @@
 #include "zgemm.cuh"
+#include <cstdlib>
 
 #ifndef ZGEMM_KT
 #define ZGEMM_KT 16   // k-tile of the large-tile variants (two shared-memory stages)
@@ -10,7 +11,9 @@
 // 128 B (op N on A / op T,C on B) or 64 B (the other cases) contiguous segments.
 //
 // One complex 8x8x4 tile product = 4 real DMMAs:  Cr += Ar*Br - Ai*Bi,  Ci += Ar*Bi + Ai*Br.
-template <int WTM, int WTN, int NWM, int NWN, int KT>
+// M3 = true: "3M" complex product, S1 = Ar Br, S2 = Ai Bi, S3 = (Ar + Ai)(Br + Bi), Re = S1 - S2, Im = S3 - S1 - S2: three real
+// DMMAs per tile product (the kernel is DMMA-bound), at the price of a third accumulator set (hence the smaller warp tile).
+template <int WTM, int WTN, int NWM, int NWN, int KT, bool M3>
 __global__ void __launch_bounds__(NWM * NWN * 32)
 zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int lda, int opA,
              const cplx* __restrict__ B, int ldb, int opB, cplx beta, cplx* __restrict__ C, int ldc) {
@@ -28,11 +31,15 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int lo = lane >> 2, lk = lane & 3;
 
-  double cr[WTM][WTN][2], ci[WTM][WTN][2];
+  // M3: cr = S1, ci = S2, c3 = S3
+  double cr[WTM][WTN][2], ci[WTM][WTN][2], c3[M3 ? WTM : 1][M3 ? WTN : 1][2];
 #pragma unroll
   for (int i = 0; i < WTM; ++i)
 #pragma unroll
-    for (int j = 0; j < WTN; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+    for (int j = 0; j < WTN; ++j) {
+      cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+      if (M3) c3[M3 ? i : 0][M3 ? j : 0][0] = c3[M3 ? i : 0][M3 ? j : 0][1] = 0.0;
+    }
 
   cplx ra[LA], rb[LB];
   auto gload = [&](int k0) {
@@ -88,15 +95,31 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
       for (int i = 0; i < WTM; ++i) a[i] = as[(kk * (BM / 8) + wm * WTM + i) * 32 + lane];
 #pragma unroll
       for (int j = 0; j < WTN; ++j) b[j] = bs[(kk * (BN / 8) + wn * WTN + j) * 32 + lane];
+      if (M3) {
+        double as3[WTM], bs3[WTN];
 #pragma unroll
-      for (int i = 0; i < WTM; ++i)
+        for (int i = 0; i < WTM; ++i) as3[i] = a[i].x + a[i].y;
 #pragma unroll
-        for (int j = 0; j < WTN; ++j) {
-          dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
-          dmma884(cr[i][j][0], cr[i][j][1], -a[i].y, b[j].y);
-          dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
-          dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
-        }
+        for (int j = 0; j < WTN; ++j) bs3[j] = b[j].x + b[j].y;
+#pragma unroll
+        for (int i = 0; i < WTM; ++i)
+#pragma unroll
+          for (int j = 0; j < WTN; ++j) {
+            dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+            dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].y);
+            dmma884(c3[M3 ? i : 0][M3 ? j : 0][0], c3[M3 ? i : 0][M3 ? j : 0][1], as3[i], bs3[j]);
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WTM; ++i)
+#pragma unroll
+          for (int j = 0; j < WTN; ++j) {
+            dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+            dmma884(cr[i][j][0], cr[i][j][1], -a[i].y, b[j].y);
+            dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+            dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+          }
+      }
     }
     if (more) sstore(stage ^ 1);   // the other stage was last read before the previous barrier
     __syncthreads();
@@ -113,7 +136,9 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
         int row = m0 + (wm * WTM + i) * 8 + lo;
         int col = n0 + (wn * WTN + j) * 8 + 2 * lk + e;
         if (row < M && col < N) {
-          cplx acc = cmul(alpha, cmake(cr[i][j][e], ci[i][j][e]));
+          const cplx prod = M3 ? cmake(cr[i][j][e] - ci[i][j][e], c3[M3 ? i : 0][M3 ? j : 0][e] - cr[i][j][e] - ci[i][j][e])
+                               : cmake(cr[i][j][e], ci[i][j][e]);
+          cplx acc = cmul(alpha, prod);
           cplx* p = C + (size_t)col * ldc + row;
           if (use_c) cfma(acc, beta, *p);
           *p = acc;
@@ -121,18 +146,18 @@ zgemm_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, int ld
       }
 }
 
-template <int WTM, int WTN, int NWM, int NWN, int KT>
+template <int WTM, int WTN, int NWM, int NWN, int KT, bool M3 = false>
 static int zgemm_launch(cudaStream_t stream, int opA, int opB, int M, int N, int K, cplx alpha, const cplx* A, int lda,
                         const cplx* B, int ldb, cplx beta, cplx* C, int ldc) {
   constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8;
   constexpr size_t smem = sizeof(cplx) * 2 * 32 * ((BM / 8) * (KT / 4) + (BN / 8) * (KT / 4));
   static bool attr = false;
   if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(zgemm_kernel<WTM, WTN, NWM, NWN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(zgemm_kernel<WTM, WTN, NWM, NWN, KT, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN);
-  zgemm_kernel<WTM, WTN, NWM, NWN, KT><<<g, NWM * NWN * 32, smem, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
+  zgemm_kernel<WTM, WTN, NWM, NWN, KT, M3><<<g, NWM * NWN * 32, smem, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
   return 0;
 }
 
@@ -143,7 +168,11 @@ int zgemm(cudaStream_t stream, int opA, int opB, int M, int N, int K, cplx alpha
   auto tiles = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
   const long want = (long)num_sms * 3 / 4;
   int rc;
-  if (tiles(128, 64) >= want) rc = zgemm_launch<4, 4, 4, 2, ZGEMM_KT>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  static const int use3m = []() { const char* e = getenv("DQMC_ZGEMM_3M"); return e ? atoi(e) : 3; }();
+  if (use3m == 1 && tiles(64, 64) >= want) rc = zgemm_launch<4, 2, 2, 4, ZGEMM_KT, true>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (use3m == 2 && tiles(128, 32) >= want) rc = zgemm_launch<4, 2, 4, 2, ZGEMM_KT, true>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (use3m == 3 && tiles(64, 64) >= want) rc = zgemm_launch<4, 2, 2, 4, 32, true>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (tiles(128, 64) >= want) rc = zgemm_launch<4, 4, 4, 2, ZGEMM_KT>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   else if (tiles(64, 64) >= want) rc = zgemm_launch<4, 2, 2, 4, ZGEMM_KT>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   else rc = zgemm_launch<2, 2, 2, 2, 8>(stream, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   if (rc) return rc;

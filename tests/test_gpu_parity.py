@@ -232,6 +232,28 @@ def test_large_size_properties(L, M):
     mc.close()
 
 
+@pytest.mark.parametrize("L", [12, 16])
+def test_full_size_greens_vs_oracle(L):
+    # BASELINE matrix sizes (n = 576, 1024) against the oracle itself, not only through properties: the stack build and the
+    # stabilized G at init, then 2*safe_mult propagations (wraps + one add_slice_sequence + calculate_greens with both
+    # factor sets non-trivial) on a short chain the CPU finishes in seconds
+    M = 30
+    mc, om = _mk(L, M, False)
+    field = np.random.RandomState(16).rand(3, L * L, M)
+    mc.init(field)
+    om.init(field)
+    assert maxabs(mc.greens, om.greens) < 1e-10
+    worst = 0.0
+    for k in range(20):
+        s, d = mc.propagate()
+        om.propagate()
+        assert (s, d) == (om.current_slice + 1, om.direction)
+        if k % 5 == 4 or k >= 9:
+            worst = max(worst, maxabs(mc.greens, om.greens))
+    assert worst < 1e-10
+    mc.close()
+
+
 # ------------------------------------------------------------------------------------------ boson action / global update
 def test_boson_action_device(golden_o3):
     # tests_O3.jl:50-59: calc_boson_action(mc, randconf) == 75.57712964980982 (and the edrun value)
