@@ -783,6 +783,7 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   a.G = c->G; a.At = c->At; a.Bm = c->Bm; a.hs = c->hs; a.nbr = c->nbr;
   a.unif = c->unif; a.nunif = c->unif_n; a.pos = c->d_pos; a.accepted = c->d_acc; a.dS = c->d_dS;
   a.flags = c->d_flags; a.bar = c->d_bar; a.prof = c->lu_prof ? c->d_prof : nullptr;
+  { static const int sym = []() { const char* e = getenv("DQMC_LU_SYM"); return e ? atoi(e) : 1; }(); a.sym = sym; }
   a.bar_mode = c->lu_bar_mode; a.bar_parity = c->lu_bar_parity; c->lu_bar_parity ^= 1;
   TRY(c, launch_local_updates(c->st, a, c->lu_grid));
   return 0;

@@ -494,13 +494,18 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       const int K = 4 * kc;
       const int lo = lane >> 2, lk = lane & 3;
       const int wm = warp & 1, wn = warp >> 1;           // 2 x 4 warps, warp tile 32 x 16
-      const int tiles_m = (n + 63) / 64, ntiles = tiles_m * tiles_m;
+      // Antiunitary flavour symmetry of the O(3) model, G = [[A, B], [-conj(B), conj(A)]] (flavour blocks (1,2 | 3,4);
+      // oracle/experiments/antiunitary_symmetry.py): every accepted update preserves it, so the flush computes the upper
+      // half of G only and writes the lower half as its mirror image - half the DMMAs, one tile per CTA at n = 1024.
+      const int hN = n >> 1;
+      const bool sym = a.sym && (hN % 64 == 0);
+      const int tiles_m = (n + 63) / 64, tiles_r = sym ? tiles_m / 2 : tiles_m, ntiles = tiles_r * tiles_m;
       const int nch = (K + 31) / 32;                     // k-chunks of 32 (at most kmax*4/32)
       // operands staged with cp.async, one commit group per k-chunk (A and B together); a CTA's tiles that share their
       // row block keep the A chunks; the G tile is fetched into registers before the DMMAs start
       int tm_loaded = -1;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int tm0 = (t % tiles_m) * 64, tn0 = (t / tiles_m) * 64;
+        const int tm0 = (t % tiles_r) * 64, tn0 = (t / tiles_r) * 64;
         const bool loadA = (tm0 != tm_loaded);
         tm_loaded = tm0;
         for (int ch = 0; ch < nch; ++ch) {
@@ -574,9 +579,15 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
-              if (row < n && col < n)
-                a.G[(size_t)col * n + row] = cmake(gv[x][y][e].x + (s1[x][y][e] - s2[x][y][e]),
-                                                   gv[x][y][e].y + (s3[x][y][e] - s1[x][y][e] - s2[x][y][e]));
+              if (row < n && col < n) {
+                const cplx v = cmake(gv[x][y][e].x + (s1[x][y][e] - s2[x][y][e]),
+                                     gv[x][y][e].y + (s3[x][y][e] - s1[x][y][e] - s2[x][y][e]));
+                a.G[(size_t)col * n + row] = v;
+                if (sym) {   // (r, c) -> (r + n/2, c + n/2) = conj(v) for c < n/2;  (r + n/2, c - n/2) = -conj(v) otherwise
+                  const bool left = col < hN;
+                  a.G[(size_t)(left ? col + hN : col - hN) * n + row + hN] = left ? cmake(v.x, -v.y) : cmake(-v.x, v.y);
+                }
+              }
             }
       }
       long long tf2 = clock64();

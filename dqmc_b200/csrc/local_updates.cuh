@@ -22,6 +22,7 @@ struct LUArgs {
   double* dS;                      // in/out: accumulated -log(exp(-dS)) of accepted proposals
   int* flags;                      // [0] stream exhausted, [1] non-real determinant ratios seen
   unsigned int* bar;               // grid barrier state: [0..1] {count, generation} (bar_mode 0); [2..3] two monotonic counters (bar_mode 1)
+  int sym;                         // 1: the flush exploits G = [[A, B], [-conj(B), conj(A)]] (upper half computed, lower half mirrored)
   int bar_mode, bar_parity;        // bar_mode 1: this launch counts on bar[2 + bar_parity] and clears bar[2 + (1 - bar_parity)]
   long long* prof;                 // optional [16] cycle counters of CTA 0 (nullptr = off)
 };
