@@ -567,7 +567,15 @@ static int calculate_greens_dev(dqmc_ctx* c) {
   TRY(c, loh_assemble(c->st, n, c->W[0], c->W[1], c->Dl, c->Dr, c->Ul, c->W[2], c->W[3], c->drp_inv, c->num_sms));
   TRY(c, qr_factor(c->st, c->W[2], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms, c->lookahead ? &c->qra : nullptr));
   TRY(c, trsm_upper(c->st, c->W[2], n, n, c->W[3], n, n, c->trsm_work, c->drp_inv, c->num_sms));
-  TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
+  // G has the antiunitary flavour symmetry [[A, B], [-conj(B), conj(A)]]: the last product is formed for the upper half of the
+  // rows only and mirrored (DQMC_GREENS_SYM=0: full product)
+  static const bool sym = []() { const char* e = getenv("DQMC_GREENS_SYM"); return e ? atoi(e) != 0 : true; }();
+  if (sym && n % 2 == 0) {
+    TRY(c, zgemm(c->st, OP_N, OP_N, n / 2, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
+    TRY(c, mirror_lower_half(c->st, c->G, n, c->num_sms));
+  } else {
+    TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
+  }
   return 0;
 }
 

@@ -498,8 +498,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
       // oracle/experiments/antiunitary_symmetry.py): every accepted update preserves it, so the flush computes the upper
       // half of G only and writes the lower half as its mirror image - half the DMMAs, one tile per CTA at n = 1024.
       const int hN = n >> 1;
-      const bool sym = a.sym && (hN % 64 == 0);
-      const int tiles_m = (n + 63) / 64, tiles_r = sym ? tiles_m / 2 : tiles_m, ntiles = tiles_r * tiles_m;
+      const bool sym = a.sym != 0;
+      const int mrows = sym ? hN : n;                    // rows of G this flush computes (the last tile row may be partial)
+      const int tiles_m = (n + 63) / 64, tiles_r = (mrows + 63) / 64, ntiles = tiles_r * tiles_m;
       const int nch = (K + 31) / 32;                     // k-chunks of 32 (at most kmax*4/32)
       // operands staged with cp.async, one commit group per k-chunk (A and B together); a CTA's tiles that share their
       // row block keep the A chunks; the G tile is fetched into registers before the DMMAs start
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
-              gv[x][y][e] = (row < n && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
+              gv[x][y][e] = (row < mrows && col < n) ? ldcg2(a.G + (size_t)col * n + row) : cmake(0.0, 0.0);
             }
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int row = tm0 + wm * 32 + x * 8 + lo, col = tn0 + wn * 16 + y * 8 + 2 * lk + e;
-              if (row < n && col < n) {
+              if (row < mrows && col < n) {
                 const cplx v = cmake(gv[x][y][e].x + (s1[x][y][e] - s2[x][y][e]),
                                      gv[x][y][e].y + (s3[x][y][e] - s1[x][y][e] - s2[x][y][e]));
                 a.G[(size_t)col * n + row] = v;

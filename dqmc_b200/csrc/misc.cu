@@ -253,3 +253,22 @@ int ew_combine(cudaStream_t st, int n, EwTerm a, EwTerm b, double alpha, cplx* o
   g_launches++;
   return 0;
 }
+
+// Lower half of a matrix with the antiunitary flavour symmetry of the O(3) model from its upper half:
+// G = [[A, B], [-conj(B), conj(A)]]  (oracle/experiments/antiunitary_symmetry.py).
+__global__ void mirror_lower_half_kernel(cplx* __restrict__ G, int n) {
+  const int h = n >> 1;
+  const size_t total = (size_t)h * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e % h), c = (int)(e / h);
+    const cplx v = G[(size_t)c * n + r];
+    const bool left = c < h;
+    G[(size_t)(left ? c + h : c - h) * n + r + h] = left ? cmake(v.x, -v.y) : cmake(-v.x, v.y);
+  }
+}
+int mirror_lower_half(cudaStream_t st, cplx* G, int n, int num_sms) {
+  mirror_lower_half_kernel<<<num_sms * 4, 256, 0, st>>>(G, n);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}

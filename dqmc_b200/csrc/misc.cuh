@@ -26,3 +26,4 @@ struct EwTerm {
   int cmode;
 };
 int ew_combine(cudaStream_t st, int n, EwTerm a, EwTerm b, double alpha, cplx* out, int num_sms);
+int mirror_lower_half(cudaStream_t st, cplx* G, int n, int num_sms);   // G = [[A, B], [-conj(B), conj(A)]] from its upper half
