@@ -334,3 +334,20 @@ def test_antiunitary_symmetry_along_oracle_sweep():
             om.local_updates(st)
             worst = max(worst, _sym_residual(om.greens))
         assert worst < 1e-12
+
+
+def test_paired_householder_udt_prototype():
+    # oracle/experiments/quaternion_qr.py (preparation of the half-matrix device path): a UDT that eliminates a column and
+    # its antiunitary partner per step, on a matrix graded over 80 orders of magnitude
+    from oracle.experiments.quaternion_qr import paired_udt, full_from_left
+    rs = np.random.RandomState(2)
+    h = 16
+    A = rs.randn(h, h) + 1j * rs.randn(h, h)
+    B = rs.randn(h, h) + 1j * rs.randn(h, h)
+    Dh = np.logspace(40, -40, h)[rs.permutation(h)]
+    X = np.block([[A, B], [-B.conj(), A.conj()]]) * np.concatenate([Dh, Dh])[None, :]
+    QL, D, TL = paired_udt(X)
+    Q, T, Df = full_from_left(QL), full_from_left(TL), np.concatenate([D, D])
+    assert maxabs(Q.conj().T @ Q, np.eye(2 * h)) < 1e-13
+    assert np.max(np.abs((Q * Df[None, :]) @ T - X) / np.linalg.norm(X, axis=0)[None, :]) < 1e-13
+    assert np.all(np.diff(D) <= 1e-12 * D[:-1]) and np.linalg.cond(T) < 1e3
