@@ -147,3 +147,71 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dataflow of the device panel kernel, emulated: like today's qr_panel_kernel (one exchange per column, everything derived
+# from RAW dot products taken before the reflector is known), a pair-step needs per remaining column c only
+#     D1_c = x^H c           = sum_q conj(x_e[q]) c_e[q] + conj(x_o[q]) c_o[q]          (all active quaternion rows q >= j)
+#     D2_c = phi(x)^H c      = sum_q x_o[q] c_e[q] - x_e[q] c_o[q]
+# plus the quaternion row j of the panel (x_e[j], x_o[j], c_e[j], c_o[j]); |x|^2 = D1_j.  With s = |x| / |q_j|,
+# (a, b) = (1 + s) (x_e[j], x_o[j]), N = |a|^2 + |b|^2:
+#     u^H c      = D1_c + s (conj(x_e[j]) c_e[j] + conj(x_o[j]) c_o[j])
+#     phi(u)^H c = D2_c + s (x_o[j] c_e[j] - x_e[j] c_o[j])
+#     d1 = w^H c      = (a u^H c + conj(b) phi(u)^H c) / N
+#     d2 = phi(w)^H c = (conj(a) phi(u)^H c - b u^H c) / N
+#     w_e[q] = (conj(a) x_e[q] + b conj(x_o[q])) / N,  w_o[q] = (conj(a) x_o[q] - b conj(x_e[q])) / N      (q > j; w[j] = (1, 0))
+#     tau = 2 / |w|^2 = 2 N / |u|^2,   |u|^2 = 2 |x| (|x| + |q_j|)
+#     c_e[q] -= tau (w_e[q] d1 + conj(w_o[q]) d2),   c_o[q] -= tau (w_o[q] d1 - conj(w_e[q]) d2)
+# The same raw dots taken against the FINISHED columns c < j (which hold w_c below their diagonal) give the Gram entries the
+# compact-WY recurrence needs, as in today's kernel:  w_c^H x = conj(D1_c),  w_c^H phi(x) = conj(D2_c)  (rows > j; add the row-j
+# term), hence  w_c^H w_j = conj(w_c,e[j]) + (conj(a) conj(D1_c') + b conj(D2_c')) / N  and the phi-partners by
+# phi(w_c)^H phi(w_j) = conj(w_c^H w_j),  phi(w_c)^H w_j = -conj(w_c^H phi(w_j)).
+# ---------------------------------------------------------------------------------------------------------------------
+def panel_rawdots(P):
+    """P: m x nc panel (pair-interleaved rows, m >= 2 nc), factorized in place with the formulas above.  Returns taus."""
+    m, nc = P.shape
+    taus = np.zeros(nc)
+    for j in range(nc):
+        t = 2 * j
+        xe, xo = P[t::2, j].copy(), P[t + 1::2, j].copy()           # active rows of the current column
+        Ce, Co = P[t::2, j + 1:], P[t + 1::2, j + 1:]                # views of the remaining columns
+        D1 = xe.conj() @ Ce + xo.conj() @ Co
+        D2 = xo @ Ce - xe @ Co
+        nx = np.sqrt((np.abs(xe) ** 2 + np.abs(xo) ** 2).sum())
+        q = np.hypot(abs(xe[0]), abs(xo[0]))
+        if nx == 0.0 or q == 0.0:
+            raise NotImplementedError("degenerate column: handled by the general routine above")
+        s = nx / q
+        a, b = (1 + s) * xe[0], (1 + s) * xo[0]
+        N = abs(a) ** 2 + abs(b) ** 2
+        uc = D1 + s * (np.conj(xe[0]) * Ce[0] + np.conj(xo[0]) * Co[0])
+        pc = D2 + s * (xo[0] * Ce[0] - xe[0] * Co[0])
+        d1 = (a * uc + np.conj(b) * pc) / N
+        d2 = (np.conj(a) * pc - b * uc) / N
+        we = (np.conj(a) * xe + b * np.conj(xo)) / N
+        wo = (np.conj(a) * xo - b * np.conj(xe)) / N
+        we[0], wo[0] = 1.0, 0.0
+        tau = 2.0 * N / (2.0 * nx * (nx + q))
+        Ce -= tau * (np.outer(we, d1) + np.outer(np.conj(wo), d2))
+        Co -= tau * (np.outer(wo, d1) - np.outer(np.conj(we), d2))
+        P[t, j], P[t + 1, j] = -s * xe[0], -s * xo[0]
+        P[t + 2::2, j], P[t + 3::2, j] = we[1:], wo[1:]
+        taus[j] = tau
+    return taus
+
+
+def check_rawdots():
+    rs = np.random.RandomState(7)
+    m, nc = 96, 16
+    P = (rs.randn(m, nc) + 1j * rs.randn(m, nc)) * np.logspace(8, -8, nc)[None, :]
+    ref = P.copy()
+    blocked_paired_qr(ref, NP=nc)                                   # only the first panel matters: h = nc columns
+    got = P.copy()
+    panel_rawdots(got)
+    print(f"panel from raw dot products vs reference panel: max rel diff {np.abs(got - ref).max() / np.abs(ref).max():.1e} "
+          f"(column-wise {np.max(np.abs(got - ref).max(axis=0) / np.abs(ref).max(axis=0)):.1e})")
+
+
+if __name__ == "__main__":
+    check_rawdots()
