@@ -66,7 +66,11 @@ int dqmc_set_neighbors(dqmc_ctx* ctx, const int64_t* neighbors);
 /* mc.p.hsfield [opdim,N,M] Float64 (parameters.jl:19) */
 int dqmc_set_hsfield(dqmc_ctx* ctx, const double* h);
 int dqmc_get_hsfield(dqmc_ctx* ctx, double* h);
-/* mc.s.greens [n,n] ComplexF64 (stack.jl:55) */
+/* mc.s.greens [n,n] ComplexF64 (stack.jl:55).
+ * The local-update flush and calculate_greens rely on the antiunitary flavour symmetry every Green's function of this model
+ * has, G = [[A, B], [-conj(B), conj(A)]] with the flavour blocks (1,2 | 3,4) (it holds for the reference's own dumped G
+ * matrices, tests/test_oracle_golden.py): they compute the upper half and write the lower half as its mirror image.  A G set
+ * through dqmc_set_greens must therefore be a physical one (or the process must run with DQMC_LU_SYM=0 DQMC_GREENS_SYM=0). */
 int dqmc_set_greens(dqmc_ctx* ctx, const double* g);
 int dqmc_get_greens(dqmc_ctx* ctx, double* g);
 /* mc.s.current_slice / mc.s.direction (stack.jl:391-499); slice in 0..M+1 */
