@@ -351,3 +351,10 @@ def test_paired_householder_udt_prototype():
     assert maxabs(Q.conj().T @ Q, np.eye(2 * h)) < 1e-13
     assert np.max(np.abs((Q * Df[None, :]) @ T - X) / np.linalg.norm(X, axis=0)[None, :]) < 1e-13
     assert np.all(np.diff(D) <= 1e-12 * D[:-1]) and np.linalg.cond(T) < 1e3
+
+
+def test_half_matrix_stabilization_prototype():
+    # oracle/experiments/half_matrix_greens.py: paired-UDT stacks, blocked paired QR with the right-hand side carried along,
+    # staircase back substitution - G from half matrices only, against the reference algorithm (beta = 10, D over 12 orders)
+    from oracle.experiments.half_matrix_greens import main
+    assert main(L=4, M=100) < 1e-12
