@@ -92,7 +92,7 @@ def main(L=4, M=400, lam=0.5):
     mc.hsfield = np.random.RandomState(3).rand(3, L * L, M)
     h = mc.n // 2
     worst = 0.0
-    for c in sorted({M // 2, M // 4, 10}):
+    for c in sorted({M // 20 * 10, M // 40 * 10, 10} - {0}):          # multiples of safe_mult: U of a finished UDT is unitary
         ref = (chain(mc, udt_geqp3, list(range(0, c)), False), chain(mc, udt_geqp3, list(range(M - 1, c - 1, -1)), True))
         mc.Ul, mc.Dl, mc.Tl = ref[0]
         mc.Ur, mc.Dr, mc.Tr = ref[1]

@@ -122,7 +122,7 @@ def main(L=4, M=40, lam=0.5):
 
     mc = oracle.OracleDQMC(oracle.Params(L=L, slices=M, safe_mult=10, Bfield=True, lam=lam))
     mc.hsfield = np.random.RandomState(3).rand(3, L * L, M)
-    for c in sorted({M // 2, M // 4, 10}):
+    for c in sorted({M // 20 * 10, M // 40 * 10, 10} - {0}):          # multiples of safe_mult
         res = {}
         for name, udt in (("geqp3", udt_geqp3), ("presort", udt_presort), ("paired", udt_paired)):
             res[name] = (chain(mc, udt, list(range(0, c)), False), chain(mc, udt, list(range(M - 1, c - 1, -1)), True))
