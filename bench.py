@@ -23,9 +23,10 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     "L16_beta40": dict(L=16, slices=400, safe_mult=10),   # BASELINE.json configs[3] (headline)
-    "L12_beta40": dict(L=12, slices=400, safe_mult=10),
-    "L8_beta20": dict(L=8, slices=200, safe_mult=10),
-    "L4_beta5": dict(L=4, slices=50, safe_mult=10),
+    "L12_beta40": dict(L=12, slices=400, safe_mult=10),   # configs[2]
+    "L8_beta20": dict(L=8, slices=200, safe_mult=10),     # configs[1]
+    "L4_beta5": dict(L=4, slices=50, safe_mult=10),       # configs[0]
+    "L20_beta40": dict(L=20, slices=400, safe_mult=10),   # configs[4] (+ time-displaced G)
 }
 MODEL = dict(hoppings="1.0,0.5,-0.5,-1.0", mu=-0.5, lam=0.5, r=2.0, c=3.0, u=1.0, delta_tau=0.1, box=0.5)
 
@@ -94,9 +95,50 @@ def synthetic_inputs(cfg, chain, nsweeps):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
+def blas_threads(n=None):
+    """Pin the BLAS/OpenMP pools of NumPy/SciPy to `n` threads (default: every host core) and return the count actually
+    set.  torchrun exports OMP_NUM_THREADS=1, which would silently turn the all-cores baseline into a one-thread one."""
+    n = n or os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        return None
+    return n
+
+
+class OracleChain:
+    """The oracle port on the FULL chain of the workload (M slices): init once (untimed), then `block()` times one
+    safe_mult block = safe_mult x {propagate; local_updates} incl. its stabilization, continuing the same Markov chain."""
+
+    def __init__(self, cfg):
+        import oracle
+        from oracle.dqmc import UniformStream
+        self.cfg = cfg
+        L, M, sm = cfg["L"], cfg["slices"], cfg["safe_mult"]
+        self.om = oracle.OracleDQMC(oracle.Params(L=L, slices=M, safe_mult=sm, lam=MODEL["lam"], all_checks=False))
+        field, _ = synthetic_inputs(cfg, 0, 0)
+        t0 = time.perf_counter()
+        self.om.init(field)
+        self.t_init = time.perf_counter() - t0
+        self.gen = np.random.Generator(np.random.Philox(5678))
+        self.UniformStream = UniformStream
+
+    def block(self):
+        L, sm = self.cfg["L"], self.cfg["safe_mult"]
+        st = self.UniformStream(self.gen.random(4 * L * L * sm))
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(sm):
+            self.om.propagate()
+            acc += self.om.local_updates(st)
+        return time.perf_counter() - t0, acc / sm
+
+
 def cpu_block_sample(cfg, nblocks=1):
     """Time `nblocks` safe_mult blocks (safe_mult x {propagate; local_updates}, one stabilization each) of the oracle
-    port on the host cores at the workload's L, on a short chain (4 blocks) so setup stays bounded; scale to a sweep."""
+    port on the host cores at the workload's L, on a short beta = 4 PROXY chain (4 blocks: the cost of a block does not
+    depend on beta, the setup does) so the bounded sample stays within seconds; scale to a sweep."""
     import oracle
     from oracle.dqmc import UniformStream
     L, sm = cfg["L"], cfg["safe_mult"]
@@ -127,23 +169,29 @@ def cpu_one_thread(cfg):
 
 
 def run_reference(args, cfg, rank, world):
+    """CPU arm: the oracle port on the workload's own chain (full M), all host cores, BLAS threads set explicitly.  Under
+    torchrun only rank 0 works: ONE CPU chain on the whole host (it is a host figure, not a per-GPU one)."""
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = blas_threads() or os.cpu_count()
+    chain = OracleChain(cfg)
+    nblk = cfg["slices"] // cfg["safe_mult"]
     times = []
     for it in range(args.warmup + args.steps):
-        t_sweep, acc = cpu_block_sample(cfg, 1)
+        t_blk, acc = chain.block()
         if it >= args.warmup:
-            times.append(t_sweep)
+            times.append(t_blk * nblk)
     t = float(np.mean(times))
     val = 1.0 / t
     line = {"impl": "reference", "metric": "sweeps/sec", "value": val, "unit": "sweeps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-            "config": {"workload": args.config, "note": "CPU restatement of the reference path (NumPy/SciPy, OpenBLAS)"},
-            "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                             "sample": "each step = 1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) "
-                                       "at the workload's L on a 4-block chain, scaled to a full sweep" % (cfg["slices"] // cfg["safe_mult"])},
+            "config": {"workload": args.config, "note": "CPU restatement of the reference path (NumPy/SciPy, OpenBLAS %d threads)" % cores,
+                       "L": cfg["L"], "slices": cfg["slices"], "safe_mult": cfg["safe_mult"]},
+            "cpu_baseline": {"value": val, "unit": "sweeps/s", "cores": cores, "blas_threads": cores, "kind": "port",
+                             "sample": "each step = 1 of the %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) "
+                                       "of the workload's own chain (full M = %d, consecutive blocks of one Markov chain; stack "
+                                       "init %.0f s untimed), x %d = one sweep" % (nblk, cfg["slices"], chain.t_init, nblk)},
             "e2e": {"value": val, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -154,8 +202,12 @@ def kernel_rooflines(mc, cfg, hbm_gbs, peak_src):
     n, N, sm = mc.n, cfg["L"] ** 2, cfg["safe_mult"]
     out = {}
     t_cublas = mc.bench_kernel(2, 5)
-    f64_peak = 8.0 * n ** 3 / (t_cublas * 1e-3) / 1e12          # measured cuBLAS ZGEMM ceiling, TFLOP/s
-    out["fp64_peak_tflops_cublas_zgemm"] = f64_peak
+    zg_n = 8.0 * n ** 3 / (t_cublas * 1e-3) / 1e12              # cuBLAS ZGEMM at the workload's n, TFLOP/s
+    dg_big = 2.0 * 4096 ** 3 / (mc.bench_kernel(13, 5) * 1e-3) / 1e12
+    zg_big = 8.0 * 4096 ** 3 / (mc.bench_kernel(14, 5) * 1e-3) / 1e12
+    f64_peak = max(zg_n, dg_big, zg_big)                        # FP64 ceiling = the best cuBLAS rate measured in this run
+    out["fp64_peak_tflops"] = f64_peak
+    out["fp64_probes_tflops"] = {"cublas_zgemm_n%d" % n: zg_n, "cublas_dgemm_4096": dg_big, "cublas_zgemm_4096": zg_big}
     t = mc.bench_kernel(6, 20)
     out["copy_G"] = {"ms": t, "GB/s": 32.0 * n * n / (t * 1e-3) / 1e9}
     t = mc.bench_kernel(0, 20)
@@ -179,7 +231,65 @@ def kernel_rooflines(mc, cfg, hbm_gbs, peak_src):
     for k, v in out.items():
         if isinstance(v, dict) and "achieved" in v:
             v["frac"] = v["achieved"] / v["peak"]
-            v["peak_source"] = peak_src if v["bound"] == "hbm" else "cuBLAS ZGEMM measured in this run"
+            v["peak_source"] = peak_src if v["bound"] == "hbm" else "best of cuBLAS DGEMM/ZGEMM measured in this run"
+    return out
+
+
+def g_vs_oracle(mc, config):
+    """max |G - G_oracle| / max |G| of the freshly initialised chain 0 on the sampled entries / probe vector the oracle
+    left in tests/golden/bench_init_<config>.npz (tests/golden/make_bench_init_golden.py), or None if there is no fixture."""
+    path = os.path.join(ROOT, "tests", "golden", f"bench_init_{config}.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    G = mc.greens
+    n = G.shape[0]
+    e_s = float(np.max(np.abs(G[np.ix_(g["rows"], g["cols"])] - g["sample"]))) / float(g["gmax"])
+    e_v = float(np.max(np.abs(G @ g["v"] - g["Gv"]))) / (float(g["gmax"]) * np.sqrt(2.0 * n))
+    return max(e_s, e_v)
+
+
+def extra_config_series(args, local_rank):
+    """The other BASELINE configs as extra series (rank 0, N=1 only): sweeps/s of configs[0..2] and configs[4] (L=20,
+    beta=40) with the time of dqmc_measure_tdgfs and the memory it holds (fermion_measurements.jl:1320-1331)."""
+    from dqmc_b200 import DQMC, Params
+    out = {}
+    for name in ("L4_beta5", "L8_beta20", "L12_beta40", "L20_beta40"):
+        cfg = CONFIGS[name]
+        L, M, sm = cfg["L"], cfg["slices"], cfg["safe_mult"]
+        p = Params(L=L, slices=M, safe_mult=sm, delta_tau=MODEL["delta_tau"], lambda_=MODEL["lam"], r=MODEL["r"], c=MODEL["c"],
+                   u=MODEL["u"], mu1=MODEL["mu"], mu2=MODEL["mu"], hoppings=MODEL["hoppings"], box=MODEL["box"],
+                   Bfield=False, all_checks=True)
+        mc = DQMC(p, device=local_rank, delay=args.delay)
+        nsw = 3
+        field, u = synthetic_inputs(cfg, 0, nsw)
+        mc.init(field)
+        mc.set_uniforms(u)
+        mc.sweep(None)
+        mc.set_timing(True); mc.timers()
+        nacc = 0
+        for _ in range(nsw - 1):
+            nacc += mc.sweep(None)[0]
+        mc.sync()
+        tm = mc.timers()
+        err, _ = mc.checks()
+        t = tm["sweep"] * 1e-3 / (nsw - 1)
+        row = {"value": 1.0 / t, "unit": "sweeps/s", "ms_per_sweep": t * 1e3, "n": mc.n, "slices": M,
+               "acceptance": nacc / ((nsw - 1) * M * L * L), "max_propagation_error": err,
+               "phases_ms_per_sweep": {k: tm[k] / (nsw - 1) for k in ("wrap", "local_updates", "stack_udt", "calculate_greens")}}
+        if name == "L20_beta40":
+            mc.set_timing(False)
+            t0 = time.perf_counter()
+            mc.measure_tdgfs()
+            mc.sync()
+            row["measure_tdgfs_s"] = time.perf_counter() - t0
+            nn16 = 16.0 * mc.n ** 2
+            row["tdgf_bytes"] = {"Gt0_G0t": 2 * M * nn16, "udt_chains": 4 * (M // sm) * (2 * nn16 + 8 * mc.n)}
+            g1, g2 = mc.Gt0(1), mc.G0t(1)
+            row["tdgf_tau0_identity_err"] = float(np.max(np.abs(g1 - g2 - np.eye(mc.n))))
+            mc.deallocate_tdgfs_stacks()
+        out[name] = row
+        mc.close()
     return out
 
 
@@ -190,7 +300,6 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         parallel.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L, M, sm = cfg["L"], cfg["slices"], cfg["safe_mult"]
     N = L * L
@@ -201,6 +310,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     nsw = args.warmup + args.steps
     field, u = synthetic_inputs(cfg, rank, nsw)
     mc.init(field)
+    g_rel = g_vs_oracle(mc, args.config) if rank == 0 else None
 
     # ---- device-resident arm: uniforms already in HBM, timed with CUDA events on the library's stream
     mc.set_uniforms(u)
@@ -240,12 +350,16 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.distributed.barrier()
     mc.sync()
     t0 = time.perf_counter()
+    chi_n, chi_s1, chi_s2 = 0, 0.0, 0.0
     for k in range(nsw_e):
         upin[:] = u_e[k * 4 * N * M:(k + 1) * 4 * N * M]
         mc.sweep(UniformStream(upin))
         _conf = mc.hsfield
+        chi = mc.measure_chi_dynamic()              # the step's measured observable: chi(q, i omega), read back every sweep
+        chi_n += 1; chi_s1 = chi_s1 + chi; chi_s2 = chi_s2 + chi * chi
     mc.sync()
     wall_e = time.perf_counter() - t0
+    chi_bytes = chi.size * 8
     if world > 1:
         tt = torch.tensor([wall_e], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
@@ -307,11 +421,14 @@ def run_ours(args, cfg, rank, world, local_rank):
         mcb.close()
 
     # ---- pooled measurement bins across chains (the path's only collective; outside the timed region)
-    h = mc.hsfield
-    phi2 = np.einsum("kis,kis->is", h, h).ravel()
-    pooled_mean, pooled_var = parallel.combined_mean_and_var(phi2.size, np.array([phi2.mean()]), np.array([phi2.var(ddof=1)]))
+    # the real observable bins: per (qy, qx, i omega) bin of chi the chain's [n, mean, var] -> one all-reduce of
+    # [n, sum x, sum |x|^2] -> pooled mean / variance exactly as statistics.jl:22-36 (boson_measurements.jl:48-56)
+    chi_mean = chi_s1 / chi_n
+    chi_var = (chi_s2 - chi_n * chi_mean ** 2) / max(chi_n - 1, 1)
+    pooled_mean, pooled_var = parallel.combined_mean_and_var(chi_n, chi_mean, chi_var)
     err, nonreal = mc.checks()
 
+    extra = extra_config_series(args, local_rank) if (rank == 0 and world == 1 and args.extra_configs) else None
     if rank == 0:
         hbm_gbs, peak_src = measured_peaks()
         kr = kernel_rooflines(mc, cfg, hbm_gbs, peak_src)
@@ -320,9 +437,13 @@ def run_ours(args, cfg, rank, world, local_rank):
         n = mc.n
         acc_rate = nacc / (args.steps * M * N)
         f_sweep = acc_rate * M * N * 32.0 * n * n + (M // sm) * 107.3 * n ** 3
+        # what the device really executes per stabilization: UDT (QR 5.33 + Q^H 8 + T-product 8) + calculate_greens
+        # (2.5 GEMMs x 8 + QR 5.33 + Q^H on the rhs 8 + triangular solve 4) = 58.7 n^3  
+        f_sweep_own = acc_rate * M * N * 32.0 * n * n + (M // sm) * 58.7 * n ** 3
         b_sweep = M * 64.0 * n * n
-        f64_peak = kr["fp64_peak_tflops_cublas_zgemm"]
+        f64_peak = kr["fp64_peak_tflops"]
         t_roof = f_sweep / (f64_peak * 1e12) + b_sweep / (hbm_gbs * 1e9)
+        t_roof_own = f_sweep_own / (f64_peak * 1e12) + b_sweep / (hbm_gbs * 1e9)
         dom = max(phases, key=phases.get)
         dom_map = {"wrap": "wrap", "stack_udt": "udt", "calculate_greens": "calculate_greens", "local_updates": None}
         if dom_map[dom] is not None:
@@ -338,10 +459,13 @@ def run_ours(args, cfg, rank, world, local_rank):
             roof = {"kernel": "local_updates_kernel", "bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
                     "frac": ach / f64_peak, "traffic": ncu_traffic("local_updates_kernel"),
                     "traffic_note": "DRAM bytes per launch (one time slice) from ncu; algorithmic flops per launch = accepted x 32 n^2",
-                    "peak_source": "cuBLAS ZGEMM measured in this run",
+                    "peak_source": "best of cuBLAS DGEMM/ZGEMM measured in this run",
+                    "limiter": "latency/issue of the serial Metropolis chain (the flush GEMMs are the only tensor work)",
                     "serial_floor_us_per_proposal": kr["local_updates_slice"]["us_per_proposal"]}
+        ncores = blas_threads() or os.cpu_count()
         t_cpu, acc_cpu = cpu_block_sample(cfg, 1)
         t_cpu1 = cpu_one_thread(cfg)
+        blas_threads()
         line = {"metric": "sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
@@ -349,21 +473,30 @@ def run_ours(args, cfg, rank, world, local_rank):
                            "L": L, "beta": M * MODEL["delta_tau"], "slices": M, "safe_mult": sm, "n": n, "delay": mc_delay(args),
                            "acceptance": acc_rate, "chains": world, "parallelism": f"{world} independent chains (replicas only)",
                            "l2": "no flush: each sweep streams the 1.3 GB UDT stack (>> 126 MB L2); G (16 MB) is L2-resident by design"},
-                "e2e": {"value": e2e, "unit": "sweeps/s", "h2d_bytes_per_step": 8 * 4 * N * M, "d2h_bytes_per_step": 8 * 3 * N * M + 24},
+                "e2e": {"value": e2e, "unit": "sweeps/s", "h2d_bytes_per_step": 8 * 4 * N * M,
+                        "d2h_bytes_per_step": 8 * 3 * N * M + 24 + chi_bytes},
                 "gpu_launches": launches, "clocks": clocks, "wall_ms_per_step": wall / args.steps * 1e3,
                 "roofline": roof,
                 "sweep_roofline": {"flops": f_sweep, "bytes": b_sweep, "t_roofline_ms": t_roof * 1e3, "frac": t_roof / (t_dev / args.steps),
+                                   "flops_note": "reference algorithm: 107.3 n^3 per stabilization (SURVEY 8d)",
+                                   "flops_executed": f_sweep_own, "frac_executed": t_roof_own / (t_dev / args.steps),
+                                   "flops_executed_note": "what the device executes: 58.7 n^3 per stabilization (DESIGN.md 4)",
                                    "fp64_peak_tflops": f64_peak, "hbm_gbs": hbm_gbs},
                 "phases_ms_per_sweep": phases, "kernels": kr, "two_chains_per_gpu": two, "bfield_on": bfield,
                 "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                                 "blas_threads": ncores,
                                  "sample": "1 of %d safe_mult blocks (10 x {propagate; local_updates}, 1 stabilization) at L=%d on a "
-                                           "4-block chain, scaled to a full sweep; oracle port, NumPy/SciPy + OpenBLAS, all host cores"
-                                           % (M // sm, L), "acceptance": acc_cpu,
-                                 "one_blas_thread": {"value": 1.0 / t_cpu1 if t_cpu1 else None, "unit": "sweeps/s", "cores": 1,
-                                                     "note": "same sample at 1 BLAS thread, the reference driver's default "
-                                                             "(app/dqmc.jl:33-37)"}},
-                "checks": {"max_propagation_error": err, "nonreal_detratios": nonreal,
-                           "pooled_phi2_mean": float(pooled_mean[0]), "pooled_phi2_var": float(pooled_var[0])}}
+                                           "beta=4 proxy chain (block cost is beta-independent), scaled to a full sweep; oracle port, "
+                                           "NumPy/SciPy + OpenBLAS, %d threads; --impl reference runs the full-M chain"
+                                           % (M // sm, L, ncores), "acceptance": acc_cpu,
+                                 "one_blas_thread_value": 1.0 / t_cpu1 if t_cpu1 else None,
+                                 "one_blas_thread_note": "same sample at 1 BLAS thread, the reference driver's default (app/dqmc.jl:33-37)"},
+                "checks": {"max_propagation_error": err, "nonreal_detratios": nonreal, "g_vs_oracle_rel": g_rel,
+                           "g_vs_oracle_note": "init G of chain 0 against the oracle's fingerprint (tests/golden/bench_init_*.npz)",
+                           "pooled_chi": {"bins": int(np.asarray(pooled_mean).size), "samples_per_chain": chi_n, "chains": world,
+                                          "chi_static_mean": float(np.asarray(pooled_mean).ravel()[0]),
+                                          "chi_static_var": float(np.asarray(pooled_var).ravel()[0])}},
+                "extra_configs": extra}
         emit(line)
     mc.close()
     if world > 1:
@@ -403,6 +536,7 @@ def main():
     ap.add_argument("--all-checks", type=int, default=1)
     ap.add_argument("--bfield-series", type=int, default=1, help="also time the sweep with the magnetic flux on (extra)")
     ap.add_argument("--two-chains", type=int, default=1, help="also time two chains per GPU (extra, not the headline)")
+    ap.add_argument("--extra-configs", type=int, default=1, help="also time the other BASELINE configs (extra series, N=1 only)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

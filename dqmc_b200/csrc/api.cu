@@ -59,7 +59,7 @@ struct dqmc_ctx {
   int* nbr;
   cplx *At, *Bm;
   double* unif;
-  long long unif_cap, unif_n;
+  long long unif_cap, unif_n, unif_pos_bound;   // unif_pos_bound: host-side upper bound of the device stream position
   long long* d_pos;
   long long* d_acc;
   double* d_dS;
@@ -75,6 +75,11 @@ struct dqmc_ctx {
   double* td_d[4];                 // [K][n]
   cplx* td_eye; double* td_ones;
   bool have_nbr, ops_ready;
+  // antiunitary flavour symmetry X = [[A, B], [-conj(B), conj(A)]]: the half-matrix shortcuts are used
+  // only while it is known to hold.  sym_model: every operator handed to dqmc_set_operator has it (checked on the host);
+  // sym_G: the current G has it (true after every calculate_greens of a symmetric model, measured for caller-supplied G).
+  bool sym_lu_opt, sym_greens_opt, sym_model, sym_G;
+  double* d_sym;                    // [2] scratch of sym_violation
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
   int lu_grid, lu_rpc;
@@ -177,6 +182,9 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   CU(c, cudaEventCreateWithFlags(&c->qra.eB, cudaEventDisableTiming));
   c->lookahead = getenv("DQMC_NO_LOOKAHEAD") == nullptr;
   { const char* e = getenv("DQMC_LU_BAR"); c->lu_bar_mode = e ? atoi(e) : 1; c->lu_bar_parity = 0; }
+  { const char* e = getenv("DQMC_LU_SYM"); c->sym_lu_opt = e ? atoi(e) != 0 : true; }
+  { const char* e = getenv("DQMC_GREENS_SYM"); c->sym_greens_opt = e ? atoi(e) != 0 : true; }
+  c->sym_model = false; c->sym_G = false;
   const size_t n = c->n, nn = n * n;
   TRY(c, dmalloc(c, &c->G, nn));
   TRY(c, dmalloc(c, &c->Gtmp, nn));
@@ -201,11 +209,11 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   CU(c, cudaMalloc((void**)&c->Bm, sizeof(cplx) * 2 * 4 * c->kmax * n));
   CU(c, cudaMemsetAsync(c->At, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
   CU(c, cudaMemsetAsync(c->Bm, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
-  c->unif = nullptr; c->unif_cap = c->unif_n = 0;
+  c->unif = nullptr; c->unif_cap = c->unif_n = c->unif_pos_bound = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
   TRY(c, dmalloc(c, &c->d_prof, 32)); c->lu_prof = false;
-  TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2));
+  TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2)); TRY(c, dmalloc(c, &c->d_sym, 2));
   c->Gt0 = c->G0t = nullptr; c->td_eye = nullptr; c->td_ones = nullptr;
   for (int i = 0; i < 4; ++i) { c->td_u[i] = c->td_t[i] = nullptr; c->td_d[i] = nullptr; }
   c->gb_G = c->gb_u_stack = c->gb_t_stack = nullptr; c->gb_d_stack = c->gb_hs = nullptr; c->gb_log_det = 0.0;
@@ -231,7 +239,7 @@ extern "C" int dqmc_destroy(dqmc_ctx* c) {
   void* ptrs[] = {c->G, c->Gtmp, c->u_stack, c->t_stack, c->d_stack, c->Ul, c->Ur, c->Tl, c->Tr, c->Dl, c->Dr,
                   c->W[0], c->W[1], c->W[2], c->W[3], c->W[4], c->tau, c->tfac, c->trsm_work, c->dabs, c->drp_inv,
                   c->colnorm, c->perm, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
-                  c->d_flags, c->d_bar, c->d_logdet, c->d_check, c->gb_G, c->gb_u_stack, c->gb_t_stack, c->gb_d_stack,
+                  c->d_flags, c->d_bar, c->d_logdet, c->d_check, c->d_sym, c->gb_G, c->gb_u_stack, c->gb_t_stack, c->gb_d_stack,
                   c->gb_hs, c->d_action, c->d_prof, c->Gt0, c->G0t, c->td_eye, c->td_ones, c->td_u[0], c->td_u[1], c->td_u[2],
                   c->td_u[3], c->td_t[0], c->td_t[1], c->td_t[2], c->td_t[3], c->td_d[0], c->td_d[1], c->td_d[2], c->td_d[3]};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -337,8 +345,35 @@ static int csc_diag(dqmc_ctx* c, const HostCSC& m, std::vector<cplx>* d) {
   return 0;
 }
 
+// Does the operator have the antiunitary flavour symmetry X[r+h, c+h] = conj(X[r, c]), X[r+h, c-h] = -conj(X[r, c]) (h = n/2)?
+static bool csc_is_antiunitary_symmetric(const HostCSC& m) {
+  const int n = m.n, h = n / 2;
+  if (n % 2) return false;
+  auto at = [&](int r, int cc) -> cplx {
+    for (int64_t k = m.colptr[cc] - 1; k < m.colptr[cc + 1] - 1; ++k) if ((int)m.rowval[k] - 1 == r) return m.nz[k];
+    return ZERO;
+  };
+  double vmax = 0.0, viol = 0.0;
+  for (int cc = 0; cc < n; ++cc)
+    for (int64_t k = m.colptr[cc] - 1; k < m.colptr[cc + 1] - 1; ++k) {
+      const int r = (int)m.rowval[k] - 1;
+      const cplx v = m.nz[k];
+      vmax = std::max(vmax, sqrt(cabs2(v)));
+      const int r2 = r < h ? r + h : r - h, c2 = cc < h ? cc + h : cc - h;
+      const cplx w = at(r2, c2);
+      const bool diag_block = (r < h) == (cc < h);
+      const cplx d = diag_block ? cmake(w.x - v.x, w.y + v.y) : cmake(w.x + v.x, w.y - v.y);
+      viol = std::max(viol, sqrt(cabs2(d)));
+    }
+  return viol <= 1e-13 * vmax;
+}
+
 static int finalize_operators(dqmc_ctx* c) {
   for (int i = 0; i <= DQMC_OP_MU_INV; ++i) if (!c->csc[i].set) return 0;   // wait until the six factors of B are there
+  c->sym_model = true;
+  for (int i = 0; i < DQMC_OP_COUNT; ++i)
+    if (c->csc[i].set && !csc_is_antiunitary_symmetric(c->csc[i])) c->sym_model = false;
+  c->sym_G = false;
   HostQuad hbh, ha, hbhinv, hainv;
   TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_HALF_B], &hbh));
   TRY(c, csc_to_quad(c, c->csc[DQMC_OP_HOP_A], &ha));
@@ -422,10 +457,20 @@ extern "C" int dqmc_get_hsfield(dqmc_ctx* c, double* h) {
   CU(c, cudaStreamSynchronize(c->st));
   return 0;
 }
+// sym_G <- does the G on the device have the antiunitary flavour symmetry (to 1e-10 of max|G|)?  Synchronises.
+static int measure_sym_G(dqmc_ctx* c) {
+  double v[2] = {0.0, 0.0};
+  if (c->n % 2) { c->sym_G = false; CU(c, cudaStreamSynchronize(c->st)); return 0; }
+  TRY(c, sym_violation(c->st, c->G, c->n, c->d_sym, c->num_sms));
+  CU(c, cudaMemcpyAsync(v, c->d_sym, sizeof(v), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->sym_G = v[0] <= 1e-10 * v[1];
+  return 0;
+}
 extern "C" int dqmc_set_greens(dqmc_ctx* c, const double* g) {
   CU(c, cudaSetDevice(c->p.device));
   CU(c, cudaMemcpyAsync(c->G, g, sizeof(cplx) * c->n * c->n, cudaMemcpyHostToDevice, c->st));
-  CU(c, cudaStreamSynchronize(c->st));
+  TRY(c, measure_sym_G(c));    // a G without the flavour symmetry switches the local updates to the full flush
   return 0;
 }
 extern "C" int dqmc_get_greens(dqmc_ctx* c, double* g) {
@@ -559,7 +604,7 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
 // calculate_greens (stack.jl:338-369): G = [1 + Ul Dl Tl (Ur Dr Tr)^†]^-1, evaluated as
 //   G = Ur Drp^-1 [ Dlp^-1 Ul^† Ur Drp^-1 + Dlm Tl Tr^† Drm ]^-1 Dlp^-1 Ul^†      (Dp = max(D,1), Dm = min(D,1))
 // with one Householder QR of the bracket (Q^† applied to the right-hand side on the fly) and a triangular solve.
-static int calculate_greens_dev(dqmc_ctx* c) {
+static int calculate_greens_dev(dqmc_ctx* c, bool allow_sym = true) {
   ScopedTimer t(c, TM_GREENS);
   const int n = c->n;
   TRY(c, zgemm(c->st, OP_C, OP_N, n, n, n, ONE, c->Ul, n, c->Ur, n, ZERO, c->W[0], n, c->num_sms));
@@ -569,7 +614,9 @@ static int calculate_greens_dev(dqmc_ctx* c) {
   TRY(c, trsm_upper(c->st, c->W[2], n, n, c->W[3], n, n, c->trsm_work, c->drp_inv, c->num_sms));
   // G has the antiunitary flavour symmetry [[A, B], [-conj(B), conj(A)]]: the last product is formed for the upper half of the
   // rows only and mirrored (DQMC_GREENS_SYM=0: full product)
-  static const bool sym = []() { const char* e = getenv("DQMC_GREENS_SYM"); return e ? atoi(e) != 0 : true; }();
+  // and only for a model whose operators have the symmetry; caller-supplied UDTs (dqmc_calculate_greens_from) get the full one)
+  const bool sym = allow_sym && c->sym_greens_opt && c->sym_model;
+  c->sym_G = c->sym_model;
   if (sym && n % 2 == 0) {
     TRY(c, zgemm(c->st, OP_N, OP_N, n / 2, n, n, ONE, c->Ur, n, c->W[3], n, ZERO, c->G, n, c->num_sms));
     TRY(c, mirror_lower_half(c->st, c->G, n, c->num_sms));
@@ -698,6 +745,11 @@ extern "C" int dqmc_propagate(dqmc_ctx* c, int32_t* slice, int32_t* direction) {
 
 extern "C" int dqmc_wrap_greens(dqmc_ctx* c, double* g, int32_t slice, int32_t direction) {
   NEED_OPS(c);
+  if (direction != 1 && direction != -1) CTX_FAIL(c, "dqmc_wrap_greens: direction must be +1 or -1");
+  // the slice matrix used is B(slice) going up and B(slice - 1) going down (stack.jl:316-325); the reference throws a
+  // BoundsError outside 1..slices
+  const int bs = direction == 1 ? slice : slice - 1;
+  if (bs < 1 || bs > c->M) CTX_FAIL(c, "dqmc_wrap_greens: slice %d with direction %d needs B(%d), outside 1..%d", slice, direction, bs, c->M);
   CU(c, cudaSetDevice(c->p.device));
   const size_t bytes = sizeof(cplx) * c->n * c->n;
   if (!g) { TRY(c, wrap_greens_dev(c, c->G, slice, direction)); return 0; }
@@ -731,10 +783,10 @@ extern "C" int dqmc_calculate_greens_from(dqmc_ctx* c, const double* Ul, const d
   CU(c, cudaMemcpyAsync(c->Ur, Ur, nn, cudaMemcpyHostToDevice, c->st));
   CU(c, cudaMemcpyAsync(c->Dr, Dr, nd, cudaMemcpyHostToDevice, c->st));
   CU(c, cudaMemcpyAsync(c->Tr, Tr, nn, cudaMemcpyHostToDevice, c->st));
-  TRY(c, calculate_greens_dev(c));
+  TRY(c, calculate_greens_dev(c, false));   // arbitrary UDTs: full product, then measure what came out
   TRY(c, calculate_logdet_dev(c));
   if (g) CU(c, cudaMemcpyAsync(g, c->G, nn, cudaMemcpyDeviceToHost, c->st));
-  CU(c, cudaStreamSynchronize(c->st));
+  TRY(c, measure_sym_G(c));
   return 0;
 }
 
@@ -768,6 +820,7 @@ static int upload_uniforms(dqmc_ctx* c, const double* u, int64_t nu) {
   }
   CU(c, cudaMemcpyAsync(c->unif, u, sizeof(double) * (size_t)nu, cudaMemcpyHostToDevice, c->st));
   c->unif_n = nu;
+  c->unif_pos_bound = 0;
   CU(c, cudaMemsetAsync(c->d_pos, 0, sizeof(long long), c->st));
   return 0;
 }
@@ -783,6 +836,12 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   ScopedTimer t(c, TM_LOCAL);
   if (!c->have_nbr) CTX_FAIL(c, "neighbour table not set (dqmc_set_neighbors)");
   if (c->current_slice < 1 || c->current_slice > c->M) CTX_FAIL(c, "local_updates: current_slice %d is not a physical slice", c->current_slice);
+  // the kernel reads a window of up to 4 N draws starting at the (device-side) stream position; positions advance by at most
+  // 4 N per slice, so a host-side upper bound is enough to refuse a launch that could run dry (it would have mutated G and
+  // the field before the error surfaced)
+  if (c->unif_n - c->unif_pos_bound < (long long)4 * c->N)
+    CTX_FAIL(c, "uniform stream exhausted: %lld draws left (upper bound), a slice may consume %d", c->unif_n - c->unif_pos_bound, 4 * c->N);
+  c->unif_pos_bound += (long long)4 * c->N;
   LUArgs a;
   a.n = c->n; a.nsites = c->N; a.nslices = c->M; a.slice = c->current_slice - 1;
   a.kmax = c->kmax; a.rpc = c->lu_rpc; a.edrun = c->p.edrun;
@@ -791,7 +850,7 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   a.G = c->G; a.At = c->At; a.Bm = c->Bm; a.hs = c->hs; a.nbr = c->nbr;
   a.unif = c->unif; a.nunif = c->unif_n; a.pos = c->d_pos; a.accepted = c->d_acc; a.dS = c->d_dS;
   a.flags = c->d_flags; a.bar = c->d_bar; a.prof = c->lu_prof ? c->d_prof : nullptr;
-  { static const int sym = []() { const char* e = getenv("DQMC_LU_SYM"); return e ? atoi(e) : 1; }(); a.sym = sym; }
+  a.sym = (c->sym_lu_opt && c->sym_model && c->sym_G && c->n % 2 == 0) ? 1 : 0;
   a.bar_mode = c->lu_bar_mode; a.bar_parity = c->lu_bar_parity; c->lu_bar_parity ^= 1;
   TRY(c, launch_local_updates(c->st, a, c->lu_grid));
   return 0;
@@ -810,6 +869,7 @@ static int counters_read(dqmc_ctx* c, int64_t* consumed, int64_t* accepted, doub
   CU(c, cudaMemcpyAsync(&ds, c->d_dS, sizeof(ds), cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaStreamSynchronize(c->st));
+  c->unif_pos_bound = pos;     // the true position replaces the upper bound
   if (consumed) *consumed = pos;
   if (accepted) *accepted = acc;
   if (dS) *dS = ds;
@@ -1190,6 +1250,9 @@ static int calc_Bchain_udts_dev(dqmc_ctx* c, int s, bool invert, bool left) {
 extern "C" int dqmc_measure_tdgfs(dqmc_ctx* c) {
   CU(c, cudaSetDevice(c->p.device));
   NEED_OPS(c);
+  if ((c->M / 2) % c->sm != 0 || c->M % 2)
+    CTX_FAIL(c, "dqmc_measure_tdgfs: slices/2 = %d must be a multiple of safe_mult = %d (fill_tdgf! starts both directions from "
+                "the stabilized slice at beta/2, fermion_measurements.jl:1513-1541)", c->M / 2, c->sm);
   TRY(c, allocate_tdgfs(c));
   const int n = c->n, M = c->M, sm = c->sm, K = M / sm;
   const size_t nn = (size_t)n * n;
@@ -1280,6 +1343,7 @@ typedef int (*cublasCreate_t)(void**);
 typedef int (*cublasDestroy_t)(void*);
 typedef int (*cublasSetStream_t)(void*, cudaStream_t);
 typedef int (*cublasZgemm_t)(void*, int, int, int, int, int, const cplx*, const cplx*, int, const cplx*, int, const cplx*, cplx*, int);
+typedef int (*cublasDgemm_t)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int);
 
 extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_per_launch) {
   CU(c, cudaSetDevice(c->p.device));
@@ -1289,19 +1353,31 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
   CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
   const bool timing_saved = c->timing;
   c->timing = false;
-  void* blas = nullptr; void* handle = nullptr; cublasZgemm_t zg = nullptr; cublasDestroy_t zdestroy = nullptr;
-  if (which == 2) {
+  void* blas = nullptr; void* handle = nullptr; cublasZgemm_t zg = nullptr; cublasDgemm_t dg = nullptr; cublasDestroy_t zdestroy = nullptr;
+  // FP64 ceilings from cuBLAS (peak probes only, never on the product path): 2 = ZGEMM at the workload's n, 13 = DGEMM and
+  // 14 = ZGEMM at 4096^3 on scratch buffers
+  const int big = 4096;
+  double* scratch = nullptr;
+  if (which == 2 || which == 13 || which == 14) {
     blas = dlopen("libcublas.so.12", RTLD_NOW | RTLD_LOCAL);
     if (!blas) blas = dlopen("libcublas.so", RTLD_NOW | RTLD_LOCAL);
     if (!blas) { c->timing = timing_saved; CTX_FAIL(c, "cuBLAS not found (peak probe only): %s", dlerror()); }
     cublasCreate_t zc = (cublasCreate_t)dlsym(blas, "cublasCreate_v2");
     cublasSetStream_t zs = (cublasSetStream_t)dlsym(blas, "cublasSetStream_v2");
     zg = (cublasZgemm_t)dlsym(blas, "cublasZgemm_v2");
+    dg = (cublasDgemm_t)dlsym(blas, "cublasDgemm_v2");
     zdestroy = (cublasDestroy_t)dlsym(blas, "cublasDestroy_v2");
-    if (!zc || !zs || !zg || zc(&handle) != 0 || zs(handle, c->st) != 0) { c->timing = timing_saved; CTX_FAIL(c, "cuBLAS init failed"); }
+    if (!zc || !zs || !zg || !dg || zc(&handle) != 0 || zs(handle, c->st) != 0) { c->timing = timing_saved; CTX_FAIL(c, "cuBLAS init failed"); }
+    if (which != 2) {
+      const size_t cnt = (size_t)big * big * (which == 14 ? 2 : 1);
+      CU(c, cudaMalloc((void**)&scratch, sizeof(double) * 3 * cnt));
+      CU(c, cudaMemsetAsync(scratch, 0, sizeof(double) * 3 * cnt, c->st));
+    }
   }
+  const double done = 1.0, dzero = 0.0;
   if (which == 0 || which == 5 || which == 7) NEED_OPS(c);
   long long pos_saved = 0;
+  const long long bound_saved = c->unif_pos_bound;
   const int slice_saved = c->current_slice;
   if (which == 5) {
     CU(c, cudaMemcpyAsync(&pos_saved, c->d_pos, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
@@ -1317,6 +1393,8 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
       case 0: rc = wrap_greens_dev(c, c->W[4], 1, 1); break;
       case 1: rc = zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[0], n, c->W[1], n, ZERO, c->W[2], n, c->num_sms); break;
       case 2: rc = zg(handle, 0, 0, n, n, n, &ONE, c->W[0], n, c->W[1], n, &ZERO, c->W[2], n); break;
+      case 13: rc = dg(handle, 0, 0, big, big, big, &done, scratch, big, scratch + (size_t)big * big, big, &dzero, scratch + (size_t)2 * big * big, big); break;
+      case 14: rc = zg(handle, 0, 0, big, big, big, &ONE, (cplx*)scratch, big, (cplx*)scratch + (size_t)big * big, big, &ZERO, (cplx*)scratch + (size_t)2 * big * big, big); break;
       case 3:
         rc = cudaMemcpyAsync(c->W[0], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
         if (!rc) rc = colnorm2(c->st, c->W[0], n, n, c->colnorm);
@@ -1325,6 +1403,7 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
       case 4: rc = calculate_greens_dev(c); break;
       case 5: {
         CU(c, cudaMemsetAsync(c->d_pos, 0, sizeof(long long), c->st));
+        c->unif_pos_bound = 0;
         rc = local_updates_dev(c, 0.5);
         break;
       }
@@ -1364,8 +1443,10 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
     CU(c, cudaMemcpyAsync(c->d_pos, &pos_saved, sizeof(long long), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaStreamSynchronize(c->st));
     c->current_slice = slice_saved;
+    c->unif_pos_bound = bound_saved;
   }
   if (handle && zdestroy) zdestroy(handle);
+  if (scratch) cudaFree(scratch);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   c->timing = timing_saved;
   if (rc) { memcpy(c->err, g_errbuf, sizeof(g_errbuf)); return -1; }

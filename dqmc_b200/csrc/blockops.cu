@@ -187,12 +187,9 @@ int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, 
   }
   const int grid = (n + nvec - 1) / nvec;
   const size_t smem = sizeof(cplx) * (size_t)nvec * ldx + tab_bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (set_max_dynamic_smem(apply_chain_kernel<false>, nullptr)) return -1;
-    if (set_max_dynamic_smem(apply_chain_kernel<true>, nullptr)) return -1;
-    attr_done = true;
-  }
+  static SmemMemo memo_cols, memo_rows;
+  if (ensure_max_dynamic_smem(apply_chain_kernel<false>, memo_cols, nullptr)) return -1;
+  if (ensure_max_dynamic_smem(apply_chain_kernel<true>, memo_rows, nullptr)) return -1;
   if (rows)
     apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2);
   else

@@ -59,6 +59,40 @@ static inline int set_max_dynamic_smem(K kernel, size_t* limit_out) {
   return 0;
 }
 
+// Function attributes are per DEVICE, and a process may hold contexts on several GPUs: every opt-in is memoised per device
+// ordinal (a process-wide flag would leave the kernels of a second device at the 48 KB default).
+#define DQMC_MAX_DEVICES 64
+struct SmemMemo { size_t lim[DQMC_MAX_DEVICES]; };   // zero-initialised static at every call site
+static inline int current_device_slot(int* dev) {
+  CUDA_TRY(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= DQMC_MAX_DEVICES) { snprintf(g_errbuf, sizeof(g_errbuf), "device ordinal %d out of range", *dev); return -1; }
+  return 0;
+}
+// largest dynamic shared memory next to the kernel's static usage; limit of the current device in *limit_out
+template <typename K>
+static inline int ensure_max_dynamic_smem(K kernel, SmemMemo& memo, size_t* limit_out) {
+  int dev = 0;
+  if (current_device_slot(&dev)) return -1;
+  if (memo.lim[dev] == 0) {
+    size_t lim = 0;
+    if (set_max_dynamic_smem(kernel, &lim)) return -1;
+    memo.lim[dev] = lim;
+  }
+  if (limit_out) *limit_out = memo.lim[dev];
+  return 0;
+}
+// fixed dynamic shared-memory size `bytes`
+template <typename K>
+static inline int ensure_dynamic_smem(K kernel, SmemMemo& memo, size_t bytes) {
+  int dev = 0;
+  if (current_device_slot(&dev)) return -1;
+  if (memo.lim[dev] < bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    memo.lim[dev] = bytes;
+  }
+  return 0;
+}
+
 // FP64 tensor-core MMA (DMMA.8x8x4): D(8x8) += A(8x4,row) * B(4x8,col).
 // lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4], d0/d1 = D[lane/4][2*(lane%4) + {0,1}].
 DQMC_D void dmma884(double& d0, double& d1, double a, double b) {

@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(256) local_updates_kernel(LUArgs a) {
   long long pf[3] = {0, 0, 0};
   long long p_s1 = 0, p_rest_acc = 0, p_rest_rej = 0, p_flush = 0, n_fl = 0, rel_prev = 0;
   __syncthreads();
+  // every CTA has read the field, the neighbour sums and the stream position: only now may CTA 0 write accepted field values
+  // back into hs (and *pos at the end).  Co-residency does not mean simultaneous start.
+  if (a.bar_mode) { bar_target += gridDim.x; grid_barrier_mono(bar_ctr, bar_target); } else grid_barrier(a.bar, gridDim.x);
   const long long t_begin = clock64();
   rel_prev = t_begin;
 
@@ -661,8 +664,9 @@ size_t local_updates_smem(const LUArgs& a) {
 
 int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid) {
   const size_t smem = local_updates_smem(a);
-  static size_t smem_lim = 0;
-  if (smem_lim == 0 && (set_max_dynamic_smem(local_updates_kernel<false>, &smem_lim) || set_max_dynamic_smem(local_updates_kernel<true>, &smem_lim))) return -1;
+  static SmemMemo memo, memo_prof;
+  size_t smem_lim = 0;
+  if (ensure_max_dynamic_smem(local_updates_kernel<false>, memo, &smem_lim) || ensure_max_dynamic_smem(local_updates_kernel<true>, memo_prof, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "local_updates: shared memory %zu > %zu", smem, smem_lim); return -1; }
   if (a.rpc > 64) { snprintf(g_errbuf, sizeof(g_errbuf), "local_updates: rows per CTA %d > 64", a.rpc); return -1; }
   LUArgs args = a;

@@ -272,3 +272,34 @@ int mirror_lower_half(cudaStream_t st, cplx* G, int n, int num_sms) {
   g_launches++;
   return 0;
 }
+
+// out[0] = max over the upper half of |G[mirror(r,c)] - mirror value of G[r,c]|, out[1] = max |G|: how far a matrix is from
+// the antiunitary flavour symmetry above (dqmc_set_greens / dqmc_calculate_greens_from decide with it whether the
+// half-matrix shortcuts may be used on caller-supplied data).
+__global__ void sym_violation_kernel(const cplx* __restrict__ G, int n, unsigned long long* __restrict__ out) {
+  const int h = n >> 1;
+  const size_t total = (size_t)h * n;
+  double mv = 0.0, mg = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e % h), c = (int)(e / h);
+    const cplx v = G[(size_t)c * n + r];
+    const bool left = c < h;
+    const cplx w = G[(size_t)(left ? c + h : c - h) * n + r + h];
+    const cplx d = left ? cmake(w.x - v.x, w.y + v.y) : cmake(w.x + v.x, w.y - v.y);
+    mv = fmax(mv, sqrt(cabs2(d)));
+    mg = fmax(mg, fmax(sqrt(cabs2(v)), sqrt(cabs2(w))));
+  }
+  mv = warp_max(mv);
+  mg = warp_max(mg);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(mv));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(mg));
+  }
+}
+int sym_violation(cudaStream_t st, const cplx* G, int n, double* out2, int num_sms) {
+  CUDA_TRY(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
+  sym_violation_kernel<<<num_sms * 4, 256, 0, st>>>(G, n, reinterpret_cast<unsigned long long*>(out2));
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}

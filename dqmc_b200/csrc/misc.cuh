@@ -27,3 +27,5 @@ struct EwTerm {
 };
 int ew_combine(cudaStream_t st, int n, EwTerm a, EwTerm b, double alpha, cplx* out, int num_sms);
 int mirror_lower_half(cudaStream_t st, cplx* G, int n, int num_sms);   // G = [[A, B], [-conj(B), conj(A)]] from its upper half
+// out2[0] = max deviation of G from that symmetry, out2[1] = max |G|
+int sym_violation(cudaStream_t st, const cplx* G, int n, double* out2, int num_sms);

@@ -598,8 +598,9 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
 long long* g_qr_prof = nullptr;
 template <int NW, int T>
 static int launch_panel_t(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* Tf, size_t smem) {
-  static size_t smem_lim = 0;
-  if (smem_lim == 0 && (set_max_dynamic_smem(qr_panel_kernel<NW, T, false>, &smem_lim) || set_max_dynamic_smem(qr_panel_kernel<NW, T, true>, &smem_lim))) return -1;
+  static SmemMemo memo, memo_prof;
+  size_t smem_lim = 0;
+  if (ensure_max_dynamic_smem(qr_panel_kernel<NW, T, false>, memo, &smem_lim) || ensure_max_dynamic_smem(qr_panel_kernel<NW, T, true>, memo_prof, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "qr panel: m=%d too large", m); return -1; }
   if (g_qr_prof) qr_panel_kernel<NW, T, true><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, g_qr_prof);
   else qr_panel_kernel<NW, T, false><<<QR_CL, NW * 32, smem, st>>>(A, lda, m, nb, tau, dabs, Tf, nullptr);
@@ -630,12 +631,9 @@ static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cp
                         int ncols) {
   if (ncols <= 0) return 0;
   if (ncols <= g_larfb_cluster_max_cols && m >= 64) {
-    static bool attr_set = false;
+    static SmemMemo memo;
     const size_t smem = sizeof(cplx) * LC_CL * 256;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(larfb_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    if (ensure_dynamic_smem(larfb_cluster_kernel, memo, smem)) return -1;
     larfb_cluster_kernel<<<((ncols + 7) / 8) * LC_CL, 256, smem, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
@@ -820,8 +818,9 @@ static int trsm_block(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, i
                       const double* rowscale) {
   const int n8 = (n + 7) / 8 * 8, lds = n8 + 4;
   const size_t smem = sizeof(cplx) * ((size_t)8 * lds + QR_NB * 8 + QR_NB * QR_NB);
-  static size_t smem_lim = 0;
-  if (smem_lim == 0 && set_max_dynamic_smem(trsm_kernel, &smem_lim)) return -1;
+  static SmemMemo memo;
+  size_t smem_lim = 0;
+  if (ensure_max_dynamic_smem(trsm_kernel, memo, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "trsm: n=%d too large", n); return -1; }
   trsm_kernel<<<(nrhs + 7) / 8, 256, smem, st>>>(A, lda, n, Y, ldy, nrhs, inv, rowscale);
   CUDA_TRY(cudaGetLastError());

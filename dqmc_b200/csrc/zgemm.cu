@@ -151,11 +151,8 @@ static int zgemm_launch(cudaStream_t stream, int opA, int opB, int M, int N, int
                         const cplx* B, int ldb, cplx beta, cplx* C, int ldc) {
   constexpr int BM = NWM * WTM * 8, BN = NWN * WTN * 8;
   constexpr size_t smem = sizeof(cplx) * 2 * 32 * ((BM / 8) * (KT / 4) + (BN / 8) * (KT / 4));
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(zgemm_kernel<WTM, WTN, NWM, NWN, KT, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static SmemMemo memo;
+  if (ensure_dynamic_smem(zgemm_kernel<WTM, WTN, NWM, NWN, KT, M3>, memo, smem)) return -1;
   dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN);
   zgemm_kernel<WTM, WTN, NWM, NWN, KT, M3><<<g, NWM * NWN * 32, smem, stream>>>(M, N, K, alpha, A, lda, opA, B, ldb, opB, beta, C, ldc);
   return 0;

@@ -57,7 +57,10 @@ int dqmc_create(dqmc_ctx** out, const dqmc_params* p);
 int dqmc_destroy(dqmc_ctx* ctx);
 const char* dqmc_last_error(dqmc_ctx* ctx);   /* ctx may be NULL: last global error */
 
-/* data of init_checkerboard_matrices[_Bfield] (hoppings_checkerboard.jl:65-136,165-270); copied */
+/* data of init_checkerboard_matrices[_Bfield] (hoppings_checkerboard.jl:65-136,165-270); Julia SparseMatrixCSC arrays
+ * (Int64, 1-based), copied.  Limit: every factor must decompose into disjoint groups of at most 4 coupled indices (a
+ * plaquette of the Assaad checkerboard, or the 4 flavours of a site); the folded multi-bond groups of CBGeneric
+ * (slice_matrices.jl:233-393) and the dense CBFalse factors are rejected with an error (out of BASELINE scope). */
 int dqmc_set_operator(dqmc_ctx* ctx, int which, int64_t m, int64_t n, const int64_t* colptr,
                       const int64_t* rowval, const void* nzval, int nz_is_complex);
 /* l.neighbors [4,N] (lattice.jl:112-117), 1-based; time neighbours are periodic (lattice.jl:144-153) */
@@ -67,10 +70,12 @@ int dqmc_set_neighbors(dqmc_ctx* ctx, const int64_t* neighbors);
 int dqmc_set_hsfield(dqmc_ctx* ctx, const double* h);
 int dqmc_get_hsfield(dqmc_ctx* ctx, double* h);
 /* mc.s.greens [n,n] ComplexF64 (stack.jl:55).
- * The local-update flush and calculate_greens rely on the antiunitary flavour symmetry every Green's function of this model
- * has, G = [[A, B], [-conj(B), conj(A)]] with the flavour blocks (1,2 | 3,4) (it holds for the reference's own dumped G
- * matrices, tests/test_oracle_golden.py): they compute the upper half and write the lower half as its mirror image.  A G set
- * through dqmc_set_greens must therefore be a physical one (or the process must run with DQMC_LU_SYM=0 DQMC_GREENS_SYM=0). */
+ * Every Green's function of this model has the antiunitary flavour symmetry G = [[A, B], [-conj(B), conj(A)]] (flavour
+ * blocks (1,2 | 3,4); it holds for the reference's own dumped G matrices, tests/test_oracle_golden.py), and the
+ * local-update flush and the last product of calculate_greens use it (upper half computed, lower half mirrored) -- but
+ * only while it is KNOWN to hold: the operators are checked for it in dqmc_set_operator, a G supplied here (or produced by
+ * dqmc_calculate_greens_from) is measured, and if it deviates by more than 1e-10 max|G| the full-matrix paths are used
+ * until the next internal calculate_greens.  Nothing is symmetrised silently. */
 int dqmc_set_greens(dqmc_ctx* ctx, const double* g);
 int dqmc_get_greens(dqmc_ctx* ctx, double* g);
 /* mc.s.current_slice / mc.s.direction (stack.jl:391-499); slice in 0..M+1 */
@@ -81,11 +86,15 @@ int dqmc_set_state(dqmc_ctx* ctx, int32_t slice, int32_t direction);
 int dqmc_build_stack(dqmc_ctx* ctx);
 /* propagate (stack.jl:391-499); returns the new (current_slice, direction) */
 int dqmc_propagate(dqmc_ctx* ctx, int32_t* slice, int32_t* direction);
-/* wrap_greens! (stack.jl:316-325) on mc.s.greens (g == NULL) or on a caller-owned host matrix */
+/* wrap_greens! (stack.jl:316-325) on mc.s.greens (g == NULL) or on a caller-owned host matrix.  direction = +1 uses
+ * B(slice), -1 uses B(slice-1); that slice must lie in 1..M (the reference throws a BoundsError), otherwise -1 is returned.
+ * Imaginary time is periodic (lattice.jl:144-153 time_neighbors): the library derives l+1 / l-1 itself and takes no
+ * time_neighbors table. */
 int dqmc_wrap_greens(dqmc_ctx* ctx, double* g_or_null, int32_t slice, int32_t direction);
 /* multiply_B_left!/right!/inv_left!/inv_right!/daggered_B_left! (slice_matrices.jl:101-226) on a host n x n matrix */
 int dqmc_multiply_B(dqmc_ctx* ctx, int op, int32_t slice, double* m);
-/* calculate_greens (stack.jl:338-369) from caller-supplied UDTs (host) into mc.s.greens; also returns it if g != NULL */
+/* calculate_greens (stack.jl:338-369) from caller-supplied UDTs (host) into mc.s.greens; also returns it if g != NULL.
+ * Arbitrary inputs are allowed: this entry always forms the full matrix (no symmetry shortcut). */
 int dqmc_calculate_greens_from(dqmc_ctx* ctx, const double* Ul, const double* Dl, const double* Tl,
                                const double* Ur, const double* Dr, const double* Tr, double* g_or_null);
 /* calculate_logdet (stack.jl:377-385) of the last calculate_greens */
@@ -118,7 +127,8 @@ int dqmc_global_update(dqmc_ctx* ctx, double box_global, const double* u, double
 /* measure_tdgfs! (fermion_measurements.jl:1343-1407, with calc_Bchain_udts! :1434-1503, inv_sum_udts_scalettar! /
  * inv_one_plus_udt_scalettar! linalg.jl:302-331,512-567, effective_greens2greens! :1125-1142 and fill_tdgf! :1509-1541):
  * G(tau,0) and G(0,tau) for all M slices of the device-resident field, kept on the device (2 M n^2 ComplexF64 + four UDT
- * chains; allocated on first use, released by dqmc_free_tdgfs = deallocate_tdgfs_stacks!). */
+ * chains; allocated on first use, released by dqmc_free_tdgfs = deallocate_tdgfs_stacks!).  slices/2 must be a multiple of
+ * safe_mult (fill_tdgf! propagates outwards from the stabilized slice at beta/2); other values return -1. */
 int dqmc_measure_tdgfs(dqmc_ctx* ctx);
 /* mc.s.meas.Gt0[slice] (which = 0) or G0t[slice] (which = 1), slice 1-based, into a host n x n matrix */
 int dqmc_get_tdgf(dqmc_ctx* ctx, int which, int32_t slice, double* out);
@@ -141,7 +151,8 @@ int dqmc_sync(dqmc_ctx* ctx);
 /* time `reps` launches of one kernel group with CUDA events on the context's stream; returns ms per launch.
  * which: 0 wrap (+1, current slice), 1 ZGEMM n x n x n (hand-written DMMA), 2 cuBLAS ZGEMM n^3 (peak probe, dlopen),
  * 3 UDT (sort+QR+Q+T), 4 calculate_greens, 5 local_updates on slice 1 with the uploaded uniforms (state restored),
- * 6 device copy of G (HBM probe), 7 add_slice_sequence B-chain (safe_mult slices) */
+ * 6 device copy of G (HBM probe), 7 add_slice_sequence B-chain (safe_mult slices), 8-12 QR / trsm pieces,
+ * 13 cuBLAS DGEMM 4096^3, 14 cuBLAS ZGEMM 4096^3 (FP64 ceilings on scratch buffers, dlopen, peak probes only) */
 int dqmc_bench_kernel(dqmc_ctx* ctx, int which, int reps, double* ms_per_launch);
 /* C = alpha*op(A)*op(B) + beta*C on host matrices through the hand-written kernel (test hook); op: 0 N, 1 T, 2 C */
 int dqmc_test_zgemm(dqmc_ctx* ctx, int opA, int opB, int M, int N, int K, const double* alpha, const double* A, int lda,

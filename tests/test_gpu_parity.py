@@ -378,3 +378,41 @@ def test_tdgfs_large_size_properties():
     assert np.isfinite(g11).all() and np.isfinite(g12).all()
     mc.deallocate_tdgfs_stacks()
     mc.close()
+
+
+# ------------------------------------------------------------------------------------------ symmetry bookkeeping
+def test_set_greens_without_flavour_symmetry():
+    # a caller-supplied G that lacks the antiunitary flavour symmetry must NOT be symmetrised by the next flush: the library
+    # measures it in dqmc_set_greens and falls back to the full-matrix flush (same arithmetic as update_greens!,
+    # local_updates.jl:61-95, on any matrix)
+    from dqmc_b200 import UniformStream
+    L, M = 4, 10
+    mc, om = _mk(L, M, False)
+    rs = np.random.RandomState(41)
+    field = rs.rand(3, L * L, M)
+    mc.init(field)
+    om.init(field)
+    g = om.greens + 0.01 * (_rand_c(rs, mc.n, mc.n) - (0.5 + 0.5j))
+    mc.greens = g
+    om.greens = g.copy()
+    u = rs.rand(4 * L * L)
+    st, ost = UniformStream(u), OracleStream(u)
+    acc_o = om.local_updates(ost)
+    acc = mc.local_updates(st)
+    assert acc == acc_o and st.consumed == ost.pos
+    assert np.array_equal(mc.hsfield, om.hsfield)
+    assert maxabs(mc.greens, om.greens) < 1e-12
+    mc.close()
+
+
+def test_wrap_greens_rejects_out_of_range_slices():
+    from dqmc_b200.lib import DqmcError
+    mc, _ = _mk(4, 10, False)
+    mc.hsfield = np.random.RandomState(1).rand(3, 16, 10)
+    g = np.eye(mc.n, dtype=complex)
+    for slc, d in ((1, -1), (11, 1), (0, 1), (5, 0)):
+        with pytest.raises(DqmcError):
+            mc.wrap_greens(g, slc, d)
+    mc.wrap_greens(g, 10, 1)
+    mc.wrap_greens(g, 2, -1)
+    mc.close()
