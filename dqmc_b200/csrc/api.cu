@@ -83,6 +83,7 @@ struct dqmc_ctx {
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
   int lu_grid, lu_rpc;
+  bool lu_blk;                      // block-lookahead local-update kernel (default when rows per CTA <= 16; DQMC_LU_KERNEL=site: the older one)
   int lu_bar_mode, lu_bar_parity;   // grid barrier of the local-update kernel: 1 = monotonic counters alternating per launch
   bool timing;
   std::vector<TimerRec> trecs;
@@ -205,10 +206,11 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->hs_bak, (size_t)3 * c->N * c->M));
   TRY(c, dmalloc(c, &c->nbr, (size_t)4 * c->N));
   // two buffers each (double-buffered by flush batch), pre-filled with the all-ones NaN sentinel the kernel spins on
-  CU(c, cudaMalloc((void**)&c->At, sizeof(cplx) * 2 * 4 * c->kmax * n));
-  CU(c, cudaMalloc((void**)&c->Bm, sizeof(cplx) * 2 * 4 * c->kmax * n));
-  CU(c, cudaMemsetAsync(c->At, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
-  CU(c, cudaMemsetAsync(c->Bm, 0xFF, sizeof(cplx) * 2 * 4 * c->kmax * n, c->st));
+  const size_t pend = sizeof(cplx) * 2 * 4 * (size_t)(c->kmax + LU_BLOCK_SITES) * n;
+  CU(c, cudaMalloc((void**)&c->At, pend));
+  CU(c, cudaMalloc((void**)&c->Bm, pend));
+  CU(c, cudaMemsetAsync(c->At, 0xFF, pend, c->st));
+  CU(c, cudaMemsetAsync(c->Bm, 0xFF, pend, c->st));
   c->unif = nullptr; c->unif_cap = c->unif_n = c->unif_pos_bound = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
   TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
@@ -221,8 +223,10 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   for (int i = 0; i < F_COUNT; ++i) { c->fop[i].nblk = 0; c->fop[i].idx = nullptr; c->fop[i].val = nullptr; }
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
   {   // the batch depth is halved until the kernel's shared memory fits (large lattices)
+    const char* e = getenv("DQMC_LU_KERNEL");
+    c->lu_blk = c->lu_rpc <= 16 && !(e && strcmp(e, "site") == 0);
     LUArgs probe; probe.nsites = c->N; probe.rpc = c->lu_rpc;
-    for (probe.kmax = c->kmax; probe.kmax > 2 && local_updates_smem(probe) > (size_t)210 * 1024; probe.kmax /= 2) { }
+    for (probe.kmax = c->kmax; probe.kmax > 2 && (c->lu_blk ? lu_block_smem(probe) : local_updates_smem(probe)) > (size_t)210 * 1024; probe.kmax /= 2) { }
     c->kmax = probe.kmax;
   }
   CU(c, cudaStreamSynchronize(c->st));
@@ -852,7 +856,7 @@ static int local_updates_dev(dqmc_ctx* c, double box) {
   a.flags = c->d_flags; a.bar = c->d_bar; a.prof = c->lu_prof ? c->d_prof : nullptr;
   a.sym = (c->sym_lu_opt && c->sym_model && c->sym_G && c->n % 2 == 0) ? 1 : 0;
   a.bar_mode = c->lu_bar_mode; a.bar_parity = c->lu_bar_parity; c->lu_bar_parity ^= 1;
-  TRY(c, launch_local_updates(c->st, a, c->lu_grid));
+  TRY(c, c->lu_blk ? launch_lu_block(c->st, a, c->lu_grid) : launch_local_updates(c->st, a, c->lu_grid));
   return 0;
 }
 

@@ -6,7 +6,8 @@
 
 struct LUArgs {
   int n, nsites, nslices, slice;   // slice 0-based
-  int kmax;                        // accepted updates batched before G is flushed with one GEMM
+  int kmax;                        // accepted updates batched before G is flushed with one GEMM (block kernel: flush at the first
+                                   // block end with more than kmax pending)
   int rpc;                         // rows of A / columns of B owned by each CTA
   int edrun;
   double box, dtau, lam_dtau, inv_dtau_c2, r, u;
@@ -27,6 +28,10 @@ struct LUArgs {
   long long* prof;                 // optional [16] cycle counters of CTA 0 (nullptr = off)
 };
 
-int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid);
+int launch_local_updates(cudaStream_t st, const LUArgs& a, int grid);   // per-site lookahead kernel (local_updates.cu)
+// block-lookahead kernel (local_updates_blk.cu): rpc <= 16, kmax <= 16; At / Bm must hold 2 x 4 (kmax + 8) x n elements
+#define LU_BLOCK_SITES 8
+int launch_lu_block(cudaStream_t st, const LUArgs& a, int grid);
+size_t lu_block_smem(const LUArgs& a);
 int local_updates_grid(int n, int num_sms, int* rpc);
 size_t local_updates_smem(const LUArgs& a);

@@ -112,3 +112,23 @@ def test_pooled_statistics_two_ranks_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "POOL_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_julia_binding_matches_header(built):
+    # integration/b200_backend.jl cannot be executed here (no julia): check it structurally -- every ccall names an exported
+    # symbol and passes as many arguments as the C prototype (lib.SIGNATURES mirrors include/dqmc_b200.h, see above) takes;
+    # function / struct / for blocks are closed
+    src = open(os.path.join(ROOT, "integration", "b200_backend.jl")).read()
+    calls = re.findall(r"ccall\(\(:(dqmc_\w+),\s*libdqmc\),\s*(\w+),\s*\(([^)]*)\)", src)
+    assert len(calls) >= 20
+    for name, ret, argt in calls:
+        assert name in built.SIGNATURES, name
+        nargs = len([a for a in argt.split(",") if a.strip()])
+        assert nargs == len(built.SIGNATURES[name][1]), (name, argt)
+        assert ret == ("Cstring" if name == "dqmc_last_error" else "Cint")
+    code = "\n".join(l.split("#")[0] for l in src.splitlines())
+    opens = len(re.findall(r"^\s*(function|struct|for|if|begin)\b", code, re.M))
+    ends = len(re.findall(r"^\s*end\s*$", code, re.M))
+    assert opens == ends, (opens, ends)
+    for fn in ("initialize_stack", "build_stack", "propagate", "local_updates", "global_update", "wrap_greens!"):
+        assert re.search(rf"function {re.escape(fn)}\(mc::AbstractDQMC\{{CBAssaadB200\}}", src), fn

@@ -145,21 +145,26 @@ np.savez({out!r}, G=mc.greens, h=mc.hsfield, nacc=nacc, consumed=consumed, ld=mc
 
 
 def test_symmetry_and_3m_switches_ab(tmp_path):
-    # the default path (antiunitary-symmetric flush, half product in calculate_greens, 3M complex products) against the plain
-    # one (DQMC_LU_SYM=0 DQMC_GREENS_SYM=0 DQMC_ZGEMM_3M=0) on a full up-down sweep at n = 576: same decisions, G to 1e-12
-    res = []
-    for tag, env in (("default", {}), ("plain", {"DQMC_LU_SYM": "0", "DQMC_GREENS_SYM": "0", "DQMC_ZGEMM_3M": "0"})):
+    # the default path (block-lookahead local updates, antiunitary-symmetric flush, half product in calculate_greens, 3M complex
+    # products) against (a) the plain one (DQMC_LU_SYM=0 DQMC_GREENS_SYM=0 DQMC_ZGEMM_3M=0) and (b) the per-site-lookahead
+    # local-update kernel (DQMC_LU_KERNEL=site) on a full up-down sweep at n = 576: same decisions, G to 1e-12
+    switches = ("DQMC_LU_SYM", "DQMC_GREENS_SYM", "DQMC_ZGEMM_3M", "DQMC_LU_KERNEL")
+    res = {}
+    for tag, env in (("default", {}), ("plain", {"DQMC_LU_SYM": "0", "DQMC_GREENS_SYM": "0", "DQMC_ZGEMM_3M": "0"}),
+                     ("site_kernel", {"DQMC_LU_KERNEL": "site"})):
         out = str(tmp_path / f"{tag}.npz")
         e = dict(os.environ)
-        for k in ("DQMC_LU_SYM", "DQMC_GREENS_SYM", "DQMC_ZGEMM_3M"):
+        for k in switches:
             e.pop(k, None)
         e.update(env)
         subprocess.run([sys.executable, "-c", _AB_SCRIPT.format(root=ROOT, out=out)], check=True, env=e, timeout=900)
-        res.append(dict(np.load(out)))
-    a, b = res
-    assert int(a["nacc"]) == int(b["nacc"]) and int(a["consumed"]) == int(b["consumed"])
-    assert np.array_equal(a["h"], b["h"])
-    d = maxabs(a["G"], b["G"]) / np.abs(b["G"]).max()
-    print(f"\nA/B default vs plain (no symmetry, no 3M): |dG|/max|G| = {d:.2e}")
-    assert d < 1e-12
-    assert np.isclose(float(a["ld"]), float(b["ld"]), rtol=1e-12)
+        res[tag] = dict(np.load(out))
+    a = res["default"]
+    for tag in ("plain", "site_kernel"):
+        b = res[tag]
+        assert int(a["nacc"]) == int(b["nacc"]) and int(a["consumed"]) == int(b["consumed"]), tag
+        assert np.array_equal(a["h"], b["h"]), tag
+        d = maxabs(a["G"], b["G"]) / np.abs(b["G"]).max()
+        print(f"\nA/B default vs {tag}: |dG|/max|G| = {d:.2e}")
+        assert d < 1e-12, tag
+        assert np.isclose(float(a["ld"]), float(b["ld"]), rtol=1e-12), tag

@@ -15,10 +15,14 @@ ms = mc.bench_kernel(5, 1)
 p = mc.lu_profile(True, read=True)
 N = L * L
 print(f"L={L} delay={delay}: {ms*1e3:.0f} us/slice  {ms*1e3/N:.2f} us/proposal")
-tot = p[0]
-print(f" cycles total {tot}  stage1 {p[1]} ({p[1]/tot:.0%})  stage2(acc) {p[2]} ({p[2]/tot:.0%})  stage2(rej) {p[6]} ({p[6]/tot:.0%})  flush iters {p[3]} ({p[3]/tot:.0%})  flushes {p[4]} accepts {p[5]}")
-print(" per-site stage1 %.0f cyc; per-accept stage2 %.0f cyc; per-reject tail %.0f; per-flush-iteration %.0f cyc" % (p[1]/N, p[2]/max(p[5]-p[4],1), p[6]/max(N-p[5],1), p[3]/max(p[4],1)))
-print(" role cycles/site: decision %.0f  prep %s  prefetch %s" % (p[8]/N, [int(p[9+k]/N) for k in range(3)], [int(p[12+k]/N) for k in range(4)]))
+import os as _os
+if _os.environ.get("DQMC_LU_KERNEL") == "site":
+    tot = p[0]
+    print(f" [site kernel] cycles total {tot}  stage1 {p[1]} ({p[1]/tot:.0%})  stage2(acc) {p[2]} ({p[2]/tot:.0%})  stage2(rej) {p[6]} ({p[6]/tot:.0%})  flush iters {p[3]} ({p[3]/tot:.0%})  flushes {p[4]} accepts {p[5]}")
+else:
+    tot = p[0]; nblk = (N + 7) // 8
+    names = ("gather", "form", "stage1", "stage2", "flush+sync")
+    print(" [block kernel] cycles total %d: " % tot + "  ".join(f"{nm} {p[1+k]} ({p[1+k]/tot:.0%})" for k, nm in enumerate(names)) + f"  flushes {p[6]} accepts {p[7]}")
+    print(" per block: gather %.0f, form %.0f; per site: stage1 %.0f; per accept: stage2 %.0f; per flush: %.0f cycles" %
+          (p[1]/nblk, p[2]/nblk, p[3]/N, p[4]/max(p[7],1), p[5]/max(p[6],1)))
 mc.close()
-print(" role-only cycles/site (before the speculative dot products): %s" % [int(p[16+k]/N) for k in range(8)])
-print(" per flush: barrier-1 %.0f, tiles %.0f, barrier-2 %.0f cycles" % tuple(p[24+k]/max(p[4],1) for k in range(3)))
