@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <map>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -30,6 +31,9 @@ struct HostCSC {
 };
 
 struct TimerRec { int cat; cudaEvent_t a, b; };
+// one stabilization step of propagate (a fixed (slice, direction) always touches the same slabs with the same kernels), captured
+// once as a CUDA graph and replayed: ~300 launches on two streams become one graph launch
+struct BlockGraph { cudaGraphExec_t exec; long long launches; int slice_after, dir_after; bool symG_after; };
 
 struct dqmc_ctx {
   dqmc_params p;
@@ -53,7 +57,7 @@ struct dqmc_ctx {
   cplx* W[5];
   cplx *tau, *tfac, *trsm_work;
   double *dabs, *drp_inv, *colnorm;
-  int* perm;
+  int *perm, *pos;
   double* hs;
   double* hs_bak;
   int* nbr;
@@ -83,9 +87,13 @@ struct dqmc_ctx {
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
   int lu_grid, lu_rpc;
+  bool udt_qrcp_sweep;              // DQMC_UDT=qrcp: the sweep's UDTs use the column-pivoted QR too (experiments / bisecting)
   bool lu_blk;                      // block-lookahead local-update kernel (default when rows per CTA <= 16; DQMC_LU_KERNEL=site: the older one)
   int lu_bar_mode, lu_bar_parity;   // grid barrier of the local-update kernel: 1 = monotonic counters alternating per launch
-  bool timing;
+  int timing;                       // 0 off, 1 sweep timer only (CUDA graphs stay on), 2 all phase timers (graphs off)
+  bool use_graphs, capturing;
+  std::map<long long, BlockGraph> graphs;
+  std::map<long long, int> graph_seen;
   std::vector<TimerRec> trecs;
   std::vector<cudaEvent_t> evpool;
   double tacc[TM_COUNT];
@@ -122,7 +130,7 @@ static cudaEvent_t ev_get(dqmc_ctx* c) {
 struct ScopedTimer {
   dqmc_ctx* c; int cat; cudaEvent_t a;
   ScopedTimer(dqmc_ctx* c_, int cat_) : c(c_), cat(cat_), a(nullptr) {
-    if (c->timing) { a = ev_get(c); cudaEventRecord(a, c->st); }
+    if (!c->capturing && c->timing >= (cat == TM_SWEEP ? 1 : 2)) { a = ev_get(c); cudaEventRecord(a, c->st); }
   }
   ~ScopedTimer() {
     if (a) { cudaEvent_t b = ev_get(c); cudaEventRecord(b, c->st); c->trecs.push_back({cat, a, b}); }
@@ -168,7 +176,9 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   c->kmax = p->delay > 0 ? p->delay : 16;
   if (c->kmax > 16) c->kmax = 16;   // the flush stages at most two k-chunks of 32 columns
   c->have_nbr = c->ops_ready = false;
-  c->timing = false;
+  c->timing = 0;
+  c->capturing = false;
+  { const char* e = getenv("DQMC_GRAPHS"); c->use_graphs = e ? atoi(e) != 0 : true; }
   for (int i = 0; i < TM_COUNT; ++i) c->tacc[i] = 0.0;
   c->current_slice = c->M + 1;
   c->direction = -1;
@@ -201,7 +211,8 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   TRY(c, dmalloc(c, &c->tfac, nblk * QR_NB * QR_NB));
   TRY(c, dmalloc(c, &c->trsm_work, nblk * QR_NB * QR_NB));
   TRY(c, dmalloc(c, &c->dabs, n)); TRY(c, dmalloc(c, &c->drp_inv, n)); TRY(c, dmalloc(c, &c->colnorm, n));
-  TRY(c, dmalloc(c, &c->perm, n));
+  TRY(c, dmalloc(c, &c->perm, n)); TRY(c, dmalloc(c, &c->pos, n));
+  { const char* e = getenv("DQMC_UDT"); c->udt_qrcp_sweep = e && strcmp(e, "qrcp") == 0; }
   TRY(c, dmalloc(c, &c->hs, (size_t)3 * c->N * c->M));
   TRY(c, dmalloc(c, &c->hs_bak, (size_t)3 * c->N * c->M));
   TRY(c, dmalloc(c, &c->nbr, (size_t)4 * c->N));
@@ -213,7 +224,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   CU(c, cudaMemsetAsync(c->Bm, 0xFF, pend, c->st));
   c->unif = nullptr; c->unif_cap = c->unif_n = c->unif_pos_bound = 0;
   TRY(c, dmalloc(c, &c->d_pos, 1)); TRY(c, dmalloc(c, &c->d_acc, 1)); TRY(c, dmalloc(c, &c->d_dS, 1));
-  TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 4));
+  TRY(c, dmalloc(c, &c->d_flags, 4)); TRY(c, dmalloc(c, &c->d_bar, 8));
   TRY(c, dmalloc(c, &c->d_prof, 32)); c->lu_prof = false;
   TRY(c, dmalloc(c, &c->d_logdet, 1)); TRY(c, dmalloc(c, &c->d_check, 2)); TRY(c, dmalloc(c, &c->d_sym, 2));
   c->Gt0 = c->G0t = nullptr; c->td_eye = nullptr; c->td_ones = nullptr;
@@ -234,15 +245,22 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   return 0;
 }
 
+static void drop_graphs(dqmc_ctx* c) {
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+  c->graph_seen.clear();
+}
+
 extern "C" int dqmc_destroy(dqmc_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->p.device);
   cudaStreamSynchronize(c->st);
   timers_resolve(c);
   for (auto e : c->evpool) cudaEventDestroy(e);
+  drop_graphs(c);
   void* ptrs[] = {c->G, c->Gtmp, c->u_stack, c->t_stack, c->d_stack, c->Ul, c->Ur, c->Tl, c->Tr, c->Dl, c->Dr,
                   c->W[0], c->W[1], c->W[2], c->W[3], c->W[4], c->tau, c->tfac, c->trsm_work, c->dabs, c->drp_inv,
-                  c->colnorm, c->perm, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
+                  c->colnorm, c->perm, c->pos, c->hs, c->hs_bak, c->nbr, c->At, c->Bm, c->unif, c->d_pos, c->d_acc, c->d_dS,
                   c->d_flags, c->d_bar, c->d_logdet, c->d_check, c->d_sym, c->gb_G, c->gb_u_stack, c->gb_t_stack, c->gb_d_stack,
                   c->gb_hs, c->d_action, c->d_prof, c->Gt0, c->G0t, c->td_eye, c->td_ones, c->td_u[0], c->td_u[1], c->td_u[2],
                   c->td_u[3], c->td_t[0], c->td_t[1], c->td_t[2], c->td_t[3], c->td_d[0], c->td_d[1], c->td_d[2], c->td_d[3]};
@@ -578,6 +596,16 @@ static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
   return 0;
 }
 
+// decompose_udt! with true column pivoting (zgeqp3 semantics, qrcp.cu): X in W[0] (destroyed) -> U, D, T (W[2]).  Slower than
+// udt_dev (level-2, one grid barrier per column) but T is as well conditioned as the reference's; used where T^-1 is applied
+// (time-displaced Green's functions), for the public dqmc_decompose_udt, and for the sweep when DQMC_UDT=qrcp.
+static int udt_qrcp_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
+  const int n = c->n;
+  TRY(c, qrcp_udt(c->st, c->W[0], n, n, c->W[1], n, c->W[2], n, Dout, c->colnorm, c->perm, c->pos, c->d_bar + 3 + 1, c->num_sms));
+  TRY(c, ew_combine(c->st, n, EwTerm{c->W[1], 1, nullptr, 0, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, 1.0, Uout, c->num_sms));
+  return 0;
+}
+
 static cplx* uslab(dqmc_ctx* c, int idx1) { return c->u_stack + (size_t)(idx1 - 1) * c->n * c->n; }
 static cplx* tslab(dqmc_ctx* c, int idx1) { return c->t_stack + (size_t)(idx1 - 1) * c->n * c->n; }
 static double* dslab(dqmc_ctx* c, int idx1) { return c->d_stack + (size_t)(idx1 - 1) * c->n; }
@@ -600,7 +628,7 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
       ch.nsteps = 0;
     }
   }
-  TRY(c, udt_dev(c, uslab(c, dst), dslab(c, dst)));
+  TRY(c, c->udt_qrcp_sweep ? udt_qrcp_dev(c, uslab(c, dst), dslab(c, dst)) : udt_dev(c, uslab(c, dst), dslab(c, dst)));
   TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[2], n, tslab(c, src), n, ZERO, tslab(c, dst), n, c->num_sms));
   return 0;
 }
@@ -673,7 +701,8 @@ extern "C" int dqmc_build_stack(dqmc_ctx* c) {
 }
 
 // propagate (stack.jl:391-499); everything is enqueued on the context's stream, nothing synchronises.
-static int propagate_dev(dqmc_ctx* c) {
+static int propagate_dev(dqmc_ctx* c);
+static int propagate_body(dqmc_ctx* c) {
   const int M = c->M, sm = c->sm;
   if (c->direction == 1) {
     if (c->current_slice % sm == 0) {
@@ -699,7 +728,7 @@ static int propagate_dev(dqmc_ctx* c) {
         TRY(c, add_slice_sequence(c, c->nel - 1, true));
         c->direction = -1;
         c->current_slice = M + 1;
-        return propagate_dev(c);
+        return propagate_body(c);
       }
     } else {
       TRY(c, wrap_greens_dev(c, c->G, c->current_slice, 1));
@@ -728,13 +757,55 @@ static int propagate_dev(dqmc_ctx* c) {
         TRY(c, add_slice_sequence(c, 1, false));
         c->direction = 1;
         c->current_slice = 0;
-        return propagate_dev(c);
+        return propagate_body(c);
       }
     } else {
       TRY(c, wrap_greens_dev(c, c->G, c->current_slice, -1));
       c->current_slice -= 1;
     }
   }
+  return 0;
+}
+
+static int propagate_dev(dqmc_ctx* c) {
+  const bool stab = c->direction == 1 ? (c->current_slice % c->sm == 0) : ((c->current_slice - 1) % c->sm == 0);
+  if (!stab || !c->use_graphs || c->timing >= 2 || c->capturing) return propagate_body(c);
+  const long long key = (long long)c->current_slice * 4 + (c->direction + 1);
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    // first visit: capture (relaxed mode: the one-off kernel attribute opt-ins of a first launch are legal inside it)
+    const long long l0 = g_launches;
+    const int s_before = c->current_slice, d_before = c->direction;
+    CU(c, cudaStreamBeginCapture(c->st, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    const int rc = propagate_body(c);
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(c->st, &g);
+    if (rc != 0 || ee != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      c->use_graphs = false;                       // fall back to eager launches for the rest of the run
+      c->current_slice = s_before; c->direction = d_before;
+      if (rc != 0) return -1;
+      return propagate_body(c);
+    }
+    BlockGraph bg;
+    const cudaError_t ei = cudaGraphInstantiate(&bg.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+      cudaGetLastError();
+      c->use_graphs = false;
+      c->current_slice = s_before; c->direction = d_before;
+      return propagate_body(c);
+    }
+    bg.launches = g_launches - l0; bg.slice_after = c->current_slice; bg.dir_after = c->direction; bg.symG_after = c->sym_G;
+    g_launches = l0;
+    it = c->graphs.emplace(key, bg).first;
+  }
+  CU(c, cudaGraphLaunch(it->second.exec, c->st));
+  g_launches += it->second.launches;
+  c->current_slice = it->second.slice_after; c->direction = it->second.dir_after; c->sym_G = it->second.symG_after;
   return 0;
 }
 
@@ -806,8 +877,7 @@ extern "C" int dqmc_decompose_udt(dqmc_ctx* c, const double* x, double* U, doubl
   const int n = c->n;
   const size_t nn = sizeof(cplx) * n * n;
   CU(c, cudaMemcpyAsync(c->W[0], x, nn, cudaMemcpyHostToDevice, c->st));
-  TRY(c, colnorm2(c->st, c->W[0], n, n, c->colnorm));
-  TRY(c, udt_dev(c, c->W[3], c->dabs));
+  TRY(c, udt_qrcp_dev(c, c->W[3], c->dabs));
   CU(c, cudaMemcpyAsync(U, c->W[3], nn, cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaMemcpyAsync(D, c->dabs, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaMemcpyAsync(T, c->W[2], nn, cudaMemcpyDeviceToHost, c->st));
@@ -977,6 +1047,7 @@ extern "C" int dqmc_calc_boson_action(dqmc_ctx* c, double* S) {
 }
 
 static void global_update_backup_swap(dqmc_ctx* c) {   // global_updates.jl:1-8 (pointer swaps, no copies)
+  drop_graphs(c);                                        // the captured graphs hold the old slab pointers
   std::swap(c->gb_u_stack, c->u_stack);
   std::swap(c->gb_d_stack, c->d_stack);
   std::swap(c->gb_t_stack, c->t_stack);
@@ -1108,8 +1179,8 @@ extern "C" int dqmc_timers(dqmc_ctx* c, double* ms, int32_t n) {
   return 0;
 }
 
-extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t enable) {
-  c->timing = enable != 0;
+extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t level) {
+  c->timing = level < 0 ? 0 : (level > 2 ? 2 : level);
   return 0;
 }
 
@@ -1236,13 +1307,12 @@ static int calc_Bchain_udts_dev(dqmc_ctx* c, int s, bool invert, bool left) {
     }
     if (rightmult) {
       if (dprev) TRY(c, ew_combine(c->st, n, EwTerm{c->W[0], 0, dprev, 1, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, 1.0, c->W[0], c->num_sms));
-      TRY(c, colnorm2(c->st, c->W[0], n, n, c->colnorm));
-      TRY(c, udt_dev(c, c->W[3], D));
+      TRY(c, udt_qrcp_dev(c, c->W[3], D));
       CU(c, cudaMemcpyAsync(T, c->W[2], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
       if (i == 0) CU(c, cudaMemcpyAsync(U, c->W[3], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
       else TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->td_u[s] + (size_t)prev * nn, n, c->W[3], n, ZERO, U, n, c->num_sms));
     } else {
-      TRY(c, udt_dev(c, U, D));
+      TRY(c, udt_qrcp_dev(c, U, D));
       if (i == 0) CU(c, cudaMemcpyAsync(T, c->W[2], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
       else TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[2], n, c->td_t[s] + (size_t)prev * nn, n, ZERO, T, n, c->num_sms));
     }
@@ -1355,8 +1425,8 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
   const size_t nn = (size_t)n * n;
   cudaEvent_t e0, e1;
   CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
-  const bool timing_saved = c->timing;
-  c->timing = false;
+  const int timing_saved = c->timing;
+  c->timing = 0;
   void* blas = nullptr; void* handle = nullptr; cublasZgemm_t zg = nullptr; cublasDgemm_t dg = nullptr; cublasDestroy_t zdestroy = nullptr;
   // FP64 ceilings from cuBLAS (peak probes only, never on the product path): 2 = ZGEMM at the workload's n, 13 = DGEMM and
   // 14 = ZGEMM at 4096^3 on scratch buffers

@@ -345,18 +345,19 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
       //     UA = (GC[:, site] - delta) M^-1 = my rows of the new columns of A, VB = Delta GR[site, :] = my columns of the new rows of B
       {
         const int q = tid & 127, ww = q >> 2, k = q & 3;
-        const bool need = (ww & 7) > j && (ww & 7) < nb;       // only the sites still to come
-        if (need) {
-          cplx acc = cmake(0.0, 0.0);
-          if (tid < 128) {
+        cplx acc = cmake(0.0, 0.0);
+        if (tid < 128) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) cfma(acc, Sw[ww * LU_SWLD + kk * 8 + j], Minv[kk * 4 + k]);   // ww is not a row of site j: no delta
-            Us[ww * 4 + k] = acc;
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[k * 4 + kk], Sw[(kk * 8 + j) * LU_SWLD + ww]);
-            Vs[k * LU_W + ww] = acc;
+          for (int kk = 0; kk < 4; ++kk) {
+            cplx g = Sw[ww * LU_SWLD + kk * 8 + j];
+            if (ww == kk * 8 + j) g.x -= 1.0;
+            cfma(acc, g, Minv[kk * 4 + k]);
           }
+          Us[ww * 4 + k] = acc;
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[k * 4 + kk], Sw[(kk * 8 + j) * LU_SWLD + ww]);
+          Vs[k * LU_W + ww] = acc;
         }
       }
       if (tid < 8 * rpt) {
@@ -383,38 +384,30 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
         }
       }
       __syncthreads();
-      // (b) Sw += U V, GC += UA V, GR += U VB on the rows / columns of the sites still to come
+      // (b) the whole window follows the update exactly: Sw += U V, GC += UA V, GR += U VB, one DMMA k-step (k = 4) per 8 x 8 tile
       if (j + 1 < nb) {
-        const int nrow = sym ? 16 : 32;
-        for (int e = tid; e < nrow * 32; e += 256) {
-          const int ww = e >> 5, wc = e & 31;                     // one warp = one row
-          if ((ww & 7) > j && (ww & 7) < nb && (wc & 7) > j && (wc & 7) < nb) {
-            cplx g = Sw[ww * LU_SWLD + wc];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cfma(g, Us[ww * 4 + k], Vs[k * LU_W + wc]);
-            Sw[ww * LU_SWLD + wc] = g;
-            if (sym) {
-              const bool left = wc < 16;
-              Sw[(ww + 16) * LU_SWLD + (left ? wc + 16 : wc - 16)] = left ? cmake(g.x, -g.y) : cmake(-g.x, g.y);
-            }
-          }
-        }
-        for (int e = tid; e < rpt * 32; e += 256) {
-          const int rl = e >> 5, wc = e & 31;
-          if ((wc & 7) > j && (wc & 7) < nb) {
-            cplx g = GC[rl * LU_SWLD + wc];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cfma(g, UAs[rl * 4 + k], Vs[k * LU_W + wc]);
-            GC[rl * LU_SWLD + wc] = g;
-          }
-        }
-        for (int e = tid; e < rpt * 32; e += 256) {
-          const int ww = e & 31, cl = e >> 5;
-          if ((ww & 7) > j && (ww & 7) < nb) {
-            cplx g = GR[ww * grld + cl];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cfma(g, Us[ww * 4 + k], VBs[k * rpt + cl]);
-            GR[ww * grld + cl] = g;
+        const int rt = rpt >> 3;
+        const int nsw = sym ? 8 : 16, ngc = rt * 4, ntl = nsw + 2 * ngc;
+        const int r = lane >> 2, kq = lane & 3, c2 = 2 * kq;
+        for (int t = warp; t < ntl; t += 8) {
+          const cplx* X; const cplx* Y; cplx* D; int ldy, ldd; bool mirror = false;
+          if (t < nsw) { const int tm = t >> 2, tnn = t & 3; X = Us + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = Sw + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; mirror = sym; }
+          else if (t < nsw + ngc) { const int qq = t - nsw, tm = qq >> 2, tnn = qq & 3; X = UAs + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = GC + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; }
+          else { const int qq = t - nsw - ngc, tm = qq & 3, tnn = qq >> 2; X = Us + tm * 8 * 4; Y = VBs + tnn * 8; ldy = rpt; D = GR + tm * 8 * grld + tnn * 8; ldd = grld; }
+          const cplx x = X[r * 4 + kq], y = Y[kq * ldy + r];
+          cplx* q0 = D + r * ldd + c2;
+          cplx v0 = q0[0], v1 = q0[1];
+          dmma884(v0.x, v1.x, x.x, y.x);
+          dmma884(v0.y, v1.y, x.x, y.y);
+          dmma884(v0.x, v1.x, -x.y, y.y);
+          dmma884(v0.y, v1.y, x.y, y.x);
+          q0[0] = v0; q0[1] = v1;
+          if (mirror) {   // t < 8: window rows tm*8 + r < 16
+            const int ww = (t >> 2) * 8 + r, wc = (t & 3) * 8 + c2;        // wc, wc + 1 lie in the same half
+            const bool left = wc < 16;
+            cplx* m0 = Sw + (ww + 16) * LU_SWLD + (left ? wc + 16 : wc - 16);
+            m0[0] = left ? cmake(v0.x, -v0.y) : cmake(-v0.x, v0.y);
+            m0[1] = left ? cmake(v1.x, -v1.y) : cmake(-v1.x, v1.y);
           }
         }
       }

@@ -26,3 +26,9 @@ int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy,
                const double* rowscale, int num_sms);
 // bench hook: the panel factorizations of qr_factor without any trailing update
 int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac);
+
+// Column-pivoted Householder QR in one cooperative kernel (qrcp.cu): the reference's decompose_udt! proper (zgeqp3).
+// A (n x n, destroyed) -> QH = Q^H, dabs = |R_jj| (descending), T = D^-1 R P^T, perm / pos = pivot order and its inverse.
+// vn: n doubles of scratch; bar: one unsigned int of scratch.
+int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, int* perm,
+             int* pos, unsigned int* bar, int num_sms);

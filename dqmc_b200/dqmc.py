@@ -338,8 +338,9 @@ class DQMC:
         self._chk(self.lib.dqmc_set_uniforms(self._ctx, _l.dptr(u), len(u)))
 
     # -- telemetry ---------------------------------------------------------------------------------------
-    def set_timing(self, enable=True):
-        self._chk(self.lib.dqmc_set_timing(self._ctx, int(enable)))
+    def set_timing(self, level=1):
+        """0 off, 1 sweep total only (CUDA graphs stay on), 2 all phase timers (graphs bypassed)."""
+        self._chk(self.lib.dqmc_set_timing(self._ctx, int(level)))
 
     def timers(self):
         ms = np.zeros(5)

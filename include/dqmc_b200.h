@@ -141,7 +141,9 @@ int dqmc_inv_sum_udts(dqmc_ctx* ctx, const double* Ua, const double* Da, const d
  * [3] calculate_greens, [4] total of dqmc_sweep; resets the accumulators.  Replaces the @mytimeit labels
  * (slice_matrices.jl:105-125, local_updates.jl:47,68, stack.jl:256,290,344). */
 int dqmc_timers(dqmc_ctx* ctx, double* ms, int32_t n);
-int dqmc_set_timing(dqmc_ctx* ctx, int32_t enable);   /* phase timers are off by default */
+/* level 0: timers off (default); 1: only the total of dqmc_sweep ([4]) -- stabilization steps keep running as captured CUDA
+ * graphs; 2: all phase timers (the graphs are bypassed so that events can be recorded between the kernels) */
+int dqmc_set_timing(dqmc_ctx* ctx, int32_t level);
 /* largest |G_wrapped - G_fresh| seen since the last call (the reference prints it when > 1e-7, stack.jl:426,477);
  * nonreal = number of proposals with |Im/Re| of the determinant ratio > 1e-4 (local_updates.jl:19-20) */
 int dqmc_checks(dqmc_ctx* ctx, double* max_propagation_error, int64_t* nonreal);

@@ -114,6 +114,34 @@ def test_decompose_udt_properties(L):
     mc.close()
 
 
+@pytest.mark.parametrize("L", [4, 8, 12])
+def test_decompose_udt_vs_lapack_geqp3(L):
+    # decompose_udt! (linalg.jl:20-39) is zgeqp3 + Q.  The device's column-pivoted Householder QR (qrcp.cu) uses the same pivot
+    # rule (largest residual norm) and the same sign convention of R_jj, with EXACT residual norms where LAPACK downdates
+    # them; on a matrix graded over 40 decades the two pivot orders agree while the norms are well separated and may differ
+    # in the tail, so: identical leading factors, and everywhere the same quality (grading of D, conditioning of T)
+    import scipy.linalg as sla
+    mc, _ = _mk(L, 10, False)
+    n = mc.n
+    rs = np.random.RandomState(8)
+    X = (_rand_c(rs, n, n) - (0.5 + 0.5j)) * np.logspace(15, -25, n)[rs.permutation(n)][None, :]
+    U, D, T = mc.decompose_udt(X)
+    Q, R, piv = sla.qr(X, pivoting=True, mode="full")
+    Dl = np.abs(np.real(np.diag(R)))
+    Tl = np.zeros_like(R)
+    Tl[:, piv] = R / Dl[:, None]
+    assert maxabs(U.conj().T @ U, np.eye(n)) < 1e-13
+    rec = (U * D[None, :]) @ T
+    assert np.max(np.abs(rec - X) / np.linalg.norm(X, axis=0)[None, :]) < 1e-13
+    assert np.all(np.diff(D) <= 1e-12 * D[:-1])
+    assert np.max(np.abs(np.log(D / Dl))) < np.log(2.0)              # same grading as LAPACK's, entry by entry
+    assert np.linalg.cond(T) < 10 * np.linalg.cond(Tl) and np.linalg.cond(T) < 1e4
+    k = 4                                                            # the leading steps are unambiguous: same pivots, same factors
+    assert np.max(np.abs(D[:k] - Dl[:k]) / Dl[:k]) < 1e-13
+    assert maxabs(U[:, :k], Q[:, :k]) < 1e-12
+    mc.close()
+
+
 def test_calculate_greens_golden(golden_o3):
     # tests_O3.jl:215-230: dumped Ur,Dr,Tr,Ul,Dl,Tl -> dumped greens, and the logdet
     mc, om = _mk(4, 10, True)
