@@ -601,7 +601,7 @@ static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
 // (time-displaced Green's functions), for the public dqmc_decompose_udt, and for the sweep when DQMC_UDT=qrcp.
 static int udt_qrcp_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
   const int n = c->n;
-  TRY(c, qrcp_udt(c->st, c->W[0], n, n, c->W[1], n, c->W[2], n, Dout, c->colnorm, c->perm, c->pos, c->d_bar + 3 + 1, c->num_sms));
+  TRY(c, qrcp_udt(c->st, c->W[0], n, n, c->W[1], n, c->W[2], n, Dout, c->colnorm, c->drp_inv, c->perm, c->pos, c->d_bar + 3 + 1, c->num_sms));
   TRY(c, ew_combine(c->st, n, EwTerm{c->W[1], 1, nullptr, 0, nullptr, 0}, EwTerm{nullptr, 0, nullptr, 0, nullptr, 0}, 1.0, Uout, c->num_sms));
   return 0;
 }

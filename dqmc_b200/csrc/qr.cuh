@@ -29,6 +29,6 @@ int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* 
 
 // Column-pivoted Householder QR in one cooperative kernel (qrcp.cu): the reference's decompose_udt! proper (zgeqp3).
 // A (n x n, destroyed) -> QH = Q^H, dabs = |R_jj| (descending), T = D^-1 R P^T, perm / pos = pivot order and its inverse.
-// vn: n doubles of scratch; bar: one unsigned int of scratch.
-int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, int* perm,
-             int* pos, unsigned int* bar, int num_sms);
+// vn, rdiag: n doubles of scratch each; bar: one unsigned int of scratch.
+int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, double* rdiag,
+             int* perm, int* pos, unsigned int* bar, int num_sms);

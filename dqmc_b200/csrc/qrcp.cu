@@ -22,7 +22,7 @@ __device__ __forceinline__ cplx ldcg_c(const cplx* p) { return __ldcg(reinterpre
 
 __global__ void __launch_bounds__(QRCP_WARPS * 32)
 qrcp_kernel(cplx* A, int lda, cplx* E, int lde, int n, double* vn, int* __restrict__ perm,
-            int* __restrict__ pos_out, double* __restrict__ dabs, unsigned int* __restrict__ bar, int staged) {
+            int* __restrict__ pos_out, double* __restrict__ dabs, double* __restrict__ rdiag, unsigned int* __restrict__ bar, int staged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* vbuf = reinterpret_cast<cplx*>(smem_raw);               // [n] current reflector (v[0] = 1)
   int* pos = reinterpret_cast<int*>(vbuf + n);                  // [n] position in the pivot order, -1 = active
@@ -111,7 +111,8 @@ qrcp_kernel(cplx* A, int lda, cplx* E, int lde, int n, double* vn, int* __restri
     if (tid == 0) pos[pc] = j;
     __syncthreads();
     if (b == pc % G && tid == 0) {                              // the owner records the step
-      A[(size_t)pc * lda + j] = cmake(beta, 0.0);               // R_jj (rows below hold the reflector in LAPACK; not needed here)
+      // R_jj = beta goes to a side array, NOT into A[j, pc]: slower CTAs may still be reading the pivot column in this step
+      rdiag[j] = beta;
       dabs[j] = fabs(beta);
       perm[j] = pc;
       pos_out[pc] = j;
@@ -152,12 +153,16 @@ qrcp_kernel(cplx* A, int lda, cplx* E, int lde, int n, double* vn, int* __restri
 }
 
 // T[i, c] = R[i, c] / dabs[i] for i <= pos[c], else 0 (columns stayed in place, so T = D^-1 R P^T needs no scatter)
-__global__ void qrcp_build_T_kernel(const cplx* __restrict__ A, int lda, int n, const double* __restrict__ dabs, const int* __restrict__ pos,
-                                    cplx* __restrict__ T, int ldt) {
+__global__ void qrcp_build_T_kernel(const cplx* __restrict__ A, int lda, int n, const double* __restrict__ dabs, const double* __restrict__ rdiag,
+                                    const int* __restrict__ pos, cplx* __restrict__ T, int ldt) {
   for (int c = blockIdx.x; c < n; c += gridDim.x) {
     const int p = pos[c];
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      T[(size_t)c * ldt + i] = (i <= p) ? cscale(A[(size_t)c * lda + i], 1.0 / dabs[i]) : cmake(0.0, 0.0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      cplx v = cmake(0.0, 0.0);
+      if (i < p) v = cscale(A[(size_t)c * lda + i], 1.0 / dabs[i]);
+      else if (i == p) v = cmake(rdiag[p] / dabs[p], 0.0);
+      T[(size_t)c * ldt + i] = v;
+    }
   }
 }
 
@@ -165,9 +170,9 @@ static size_t qrcp_smem_base(int n) { return (((size_t)n * (sizeof(cplx) + sizeo
 size_t qrcp_smem(int n, bool staged) { return qrcp_smem_base(n) + (staged ? sizeof(cplx) * (size_t)QRCP_WARPS * n : 0); }
 
 // A (n x n, destroyed: R in the rows i <= pos[c] of every column c) -> QH = Q^H (n x n), dabs = |R_jj|, pos / perm, T = D^-1 R P^T.
-// vn: n doubles, bar: one zero-initialised unsigned int (reset here).
-int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, int* perm,
-             int* pos, unsigned int* bar, int num_sms) {
+// vn, rdiag: n doubles of scratch each, bar: one unsigned int (reset here).
+int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, double* rdiag,
+             int* perm, int* pos, unsigned int* bar, int num_sms) {
   static SmemMemo memo;
   size_t lim = 0;
   if (ensure_max_dynamic_smem(qrcp_kernel, memo, &lim)) return -1;
@@ -178,10 +183,10 @@ int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* 
   CUDA_TRY(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
   int grid = num_sms;
   if (grid > 2 * n) grid = 2 * n;
-  void* params[] = {&A, &lda, &QH, &ldq, &n, &vn, &perm, &pos, &dabs, &bar, &staged};
+  void* params[] = {&A, &lda, &QH, &ldq, &n, &vn, &perm, &pos, &dabs, &rdiag, &bar, &staged};
   CUDA_TRY(cudaLaunchCooperativeKernel((const void*)qrcp_kernel, dim3(grid), dim3(QRCP_WARPS * 32), params, smem, st));
   g_launches++;
-  qrcp_build_T_kernel<<<min(n, num_sms * 8), 256, 0, st>>>(A, lda, n, dabs, pos, T, ldt);
+  qrcp_build_T_kernel<<<min(n, num_sms * 8), 256, 0, st>>>(A, lda, n, dabs, rdiag, pos, T, ldt);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
