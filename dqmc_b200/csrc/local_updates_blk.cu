@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
   cplx* VBs = reinterpret_cast<cplx*>(un + Lo.u_VB);              // [4][rpt]
   cplx* FA = reinterpret_cast<cplx*>(un + Lo.u_FA);               // flush staging (aliases the window: dead during a flush)
   cplx* FB = reinterpret_cast<cplx*>(un + Lo.u_FB);
-  __shared__ cplx Mm[16], Cof[16], Minv[16];
+  __shared__ cplx Mm[16], Cof[16], g4s[16], X1s[16], X2s[16], T1s[16], T2s[16];
+  __shared__ cplx Minv2[2][16], Dl2[2][16];                       // M^-1 and Delta of the site being applied (double-buffered by site parity)
   __shared__ Prep prep[2][3];
-  __shared__ int s_accept, s_scn, s_exh;
+  __shared__ int s_accept2[2], s_scn2[2], s_exh;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * rpc;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
   long long nacc = 0;
   double dS_sum = 0.0;
   int kc = 0, np = 0, batch = 0, nonreal = 0, s_cur = 0;
+  long long pf[5] = {0, 0, 0, 0, 0};                         // PROF, per flush: barrier 1, staging + DMMA, G read-modify-write, barrier 2, re-arm
   long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};               // PROF: [0] gather [1] form [2] stage 1 [3] stage 2 [4] flush [5] #flush
   __syncthreads();
   // every CTA has read the field, the neighbour sums and the stream position: only now may CTA 0 write accepted field values
@@ -164,15 +166,12 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
   if (warp == 1) do_prep(a, fs, tn, nbr, uw, 0, navail, 0, -1, 0.0, 0.0, 0.0, &prep[0][0], &s_exh);
   __syncthreads();
 
-  int s0 = 0, nb = 0;                                       // current block: first site, number of sites
-  for (int i = 0; i < N; ++i) {
-    const int b = i & 1, nbuf = b ^ 1;
-    const bool have_next = (i + 1 < N);
+  for (int s0 = 0; s0 < N; s0 += LU_BS) {
+    const int nb = min(LU_BS, N - s0);                        // sites of this block
     cplx* Atw = a.At + batch * bufstride;
     cplx* Bmw = a.Bm + batch * bufstride;
     // ================= block start: gather the window, form Sw / GC / GR =================
-    if (i == s0 + nb) {
-      s0 = i; nb = min(LU_BS, N - s0);
+    {
       long long t0 = PROF ? clock64() : 0;
       {
         // (1) pending columns: thread = (window index w, 8 threads per row), all loads in flight before the first check
@@ -277,149 +276,205 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
       }
       if (PROF) { const long long t2 = clock64(); pr[0] += t1 - t0; pr[1] += t2 - t1; }
     }
-    const int j = i - s0;                                   // position inside the block
     long long ts0 = PROF ? clock64() : 0;
-    // ================= stage 1: decision for site i (warp 0) | proposal of site i+1 under 3 scenarios (warps 1-3) =================
-    if (warp == 0) {
-      const Prep& P = prep[b][s_cur];
-      const int r = (lane >> 2) & 3, c = lane & 3;
-      if (lane < 16) {   // M = 1 + Delta * (1 - G_eff[site block])
-        const cplx* col = Sw + (c * 8 + j);                 // Sw[k*8+j][c*8+j], k = 0..3
-        cplx g0 = col[(0 * 8 + j) * LU_SWLD], g1 = col[(1 * 8 + j) * LU_SWLD], g2 = col[(2 * 8 + j) * LU_SWLD], g3 = col[(3 * 8 + j) * LU_SWLD];
-        g0 = cmake((c == 0 ? 1.0 : 0.0) - g0.x, -g0.y);
-        g1 = cmake((c == 1 ? 1.0 : 0.0) - g1.x, -g1.y);
-        g2 = cmake((c == 2 ? 1.0 : 0.0) - g2.x, -g2.y);
-        g3 = cmake((c == 3 ? 1.0 : 0.0) - g3.x, -g3.y);
-        const cplx t0 = cmul(P.D[r * 4 + 0], g0), t1 = cmul(P.D[r * 4 + 1], g1);
-        const cplx t2 = cmul(P.D[r * 4 + 2], g2), t3 = cmul(P.D[r * 4 + 3], g3);
-        cplx m = cadd(cadd(t0, t1), cadd(t2, t3));
-        if (r == c) m.x += 1.0;
-        Mm[r * 4 + c] = m;
-      }
-      __syncwarp();
-      if (lane < 16) {   // cofactor (r,c)
-        const int r0 = (r == 0) ? 1 : 0, r1 = (r <= 1) ? 2 : 1, r2 = (r <= 2) ? 3 : 2;
-        const int c0 = (c == 0) ? 1 : 0, c1 = (c <= 1) ? 2 : 1, c2 = (c <= 2) ? 3 : 2;
-        cplx d = det3(Mm[r0 * 4 + c0], Mm[r0 * 4 + c1], Mm[r0 * 4 + c2], Mm[r1 * 4 + c0], Mm[r1 * 4 + c1], Mm[r1 * 4 + c2],
-                      Mm[r2 * 4 + c0], Mm[r2 * 4 + c1], Mm[r2 * 4 + c2]);
-        Cof[r * 4 + c] = ((r + c) & 1) ? cneg(d) : d;
-      }
-      __syncwarp();
-      const cplx p0 = cmul(Mm[0], Cof[0]), p1 = cmul(Mm[1], Cof[1]), p2 = cmul(Mm[2], Cof[2]), p3 = cmul(Mm[3], Cof[3]);
-      const cplx det = cadd(cadd(p0, p1), cadd(p2, p3));     // expansion along row 0
-      const double p_acc = P.e_dS * det.x;
-      int acc_flag, scn;
-      if (p_acc > 1.0) { acc_flag = 1; scn = 1; }
-      else { acc_flag = (P.u3 < p_acc) ? 1 : 0; scn = acc_flag ? 2 : 0; }
-      if (lane == 0) { s_accept = acc_flag; s_scn = scn; }
-      if (acc_flag) {
-        if (lane < 16) {
-          const double id = 1.0 / (det.x * det.x + det.y * det.y);
-          const cplx dinv = cmake(det.x * id, -det.y * id);
-          Minv[r * 4 + c] = cmul(Cof[c * 4 + r], dinv);
+    // ================= the sites of the block: three roles, no CTA-wide barrier =================
+    //   warp 0      decides site j from its private copy g4s of the site's 4x4 block of G_eff, then derives the block of site
+    //               j+1 itself (Sw as of site j-1 plus the rank-4 term of site j), so the next decision never waits for the
+    //               window update of the current one;
+    //   warps 1-3   proposal of site j+1 under the three possible outcomes of site j;
+    //   warps 4-7   window update of site j (U, V, rank-4 DMMA tiles on Sw, GC, GR; my slice of the new columns of A / rows of
+    //               B appended and published), overlapped with the decision of site j+1.
+    // Named barriers: P (warps 0-3, once per site), GO (warp 0 arrives, warps 4-7 wait: "site j decided"), DONE (warps 4-7
+    // arrive, warp 0 waits: "window exact up to site j"), UPD (warps 4-7).
+    if (warp == 0 && lane < 16) g4s[lane] = Sw[((lane >> 2) * 8) * LU_SWLD + (lane & 3) * 8];     // block of site s0: [r*4+c]
+    __syncwarp();
+    for (int j = 0; j < nb; ++j) {
+      const int i = s0 + j, b = i & 1, nbuf = b ^ 1, jb = j & 1;
+      const bool have_next = (i + 1 < N);
+      int accepted, scn;
+      if (warp == 0) {
+        const Prep& P = prep[b][s_cur];
+        const int r = (lane >> 2) & 3, c = lane & 3;
+        if (lane < 16) {   // M = 1 + Delta * (1 - G_eff[site block])
+          cplx g0 = g4s[0 + c], g1 = g4s[4 + c], g2 = g4s[8 + c], g3 = g4s[12 + c];
+          g0 = cmake((c == 0 ? 1.0 : 0.0) - g0.x, -g0.y);
+          g1 = cmake((c == 1 ? 1.0 : 0.0) - g1.x, -g1.y);
+          g2 = cmake((c == 2 ? 1.0 : 0.0) - g2.x, -g2.y);
+          g3 = cmake((c == 3 ? 1.0 : 0.0) - g3.x, -g3.y);
+          const cplx t0 = cmul(P.D[r * 4 + 0], g0), t1 = cmul(P.D[r * 4 + 1], g1);
+          const cplx t2 = cmul(P.D[r * 4 + 2], g2), t3 = cmul(P.D[r * 4 + 3], g3);
+          cplx m = cadd(cadd(t0, t1), cadd(t2, t3));
+          if (r == c) m.x += 1.0;
+          Mm[r * 4 + c] = m;
         }
-        nacc++;
-        dS_sum += P.mlog;
+        __syncwarp();
+        if (lane < 16) {   // cofactor (r,c)
+          const int r0 = (r == 0) ? 1 : 0, r1 = (r <= 1) ? 2 : 1, r2 = (r <= 2) ? 3 : 2;
+          const int c0 = (c == 0) ? 1 : 0, c1 = (c <= 1) ? 2 : 1, c2 = (c <= 2) ? 3 : 2;
+          cplx d = det3(Mm[r0 * 4 + c0], Mm[r0 * 4 + c1], Mm[r0 * 4 + c2], Mm[r1 * 4 + c0], Mm[r1 * 4 + c1], Mm[r1 * 4 + c2],
+                        Mm[r2 * 4 + c0], Mm[r2 * 4 + c1], Mm[r2 * 4 + c2]);
+          Cof[r * 4 + c] = ((r + c) & 1) ? cneg(d) : d;
+        }
+        __syncwarp();
+        const cplx p0 = cmul(Mm[0], Cof[0]), p1 = cmul(Mm[1], Cof[1]), p2 = cmul(Mm[2], Cof[2]), p3 = cmul(Mm[3], Cof[3]);
+        const cplx det = cadd(cadd(p0, p1), cadd(p2, p3));     // expansion along row 0
+        const double p_acc = P.e_dS * det.x;
+        if (p_acc > 1.0) { accepted = 1; scn = 1; }
+        else { accepted = (P.u3 < p_acc) ? 1 : 0; scn = accepted ? 2 : 0; }
+        if (lane == 0) { s_accept2[jb] = accepted; s_scn2[jb] = scn; }
+        cplx minv = cmake(0.0, 0.0);
+        if (accepted) {
+          if (lane < 16) {
+            const double id = 1.0 / (det.x * det.x + det.y * det.y);
+            const cplx dinv = cmake(det.x * id, -det.y * id);
+            minv = cmul(Cof[c * 4 + r], dinv);
+            Minv2[jb][r * 4 + c] = minv;
+            Dl2[jb][lane] = P.D[lane];
+          }
+          if (lane < 3) {
+            fs[3 * i + lane] = P.nw[lane];
+            if (blockIdx.x == 0) a.hs[(size_t)3 * N * sl + 3 * i + lane] = P.nw[lane];
+          }
+          nacc++;
+          dS_sum += P.mlog;
+        }
+        if (fabs(det.y) > 1e-4 * fabs(det.x)) nonreal++;
+        __syncwarp();
+        if (j > 0) asm volatile("bar.sync 3, 160;" ::: "memory");        // DONE(j-1): the window is exact up to site j-1
+        // what the block of site j+1 needs from the window, read BEFORE the update of site j may start
+        cplx blk = cmake(0.0, 0.0), x1 = blk, x2 = blk;
+        if (j + 1 < nb && lane < 16) {
+          blk = Sw[(r * 8 + j + 1) * LU_SWLD + c * 8 + j + 1];
+          x1 = Sw[(r * 8 + j + 1) * LU_SWLD + c * 8 + j];                 // X1[r][kk = c] = G_eff[row r of site j+1, col kk of site j]
+          x2 = Sw[(r * 8 + j) * LU_SWLD + c * 8 + j + 1];                 // X2[kk = r][c] = G_eff[row kk of site j, col c of site j+1]
+        }
+        asm volatile("bar.arrive 2, 160;" ::: "memory");                  // GO(j)
+        if (j + 1 < nb) {
+          if (accepted) {   // g4(j+1) = blk + (X1 M^-1)(Delta X2)
+            if (lane < 16) { X1s[lane] = x1; X2s[lane] = x2; }
+            __syncwarp();
+            if (lane < 16) {
+              cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) cfma(acc, X1s[r * 4 + kk], Minv2[jb][kk * 4 + c]);
+              T1s[lane] = acc;
+            } else {
+              cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[r * 4 + kk], X2s[kk * 4 + c]);
+              T2s[lane - 16] = acc;
+            }
+            __syncwarp();
+            if (lane < 16) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) cfma(blk, T1s[r * 4 + kk], T2s[kk * 4 + c]);
+            }
+          }
+          if (lane < 16) g4s[lane] = blk;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");                    // P(j)
+      } else if (warp <= 3) {
+        if (have_next) {
+          const int sc = warp - 1;                                  // 0 rejected, 1 accepted (no draw), 2 accepted (draw)
+          const Prep& Pc = prep[b][s_cur];
+          do_prep(a, fs, tn, nbr, uw, off + (sc == 1 ? 3 : 4), navail, i + 1, sc == 0 ? -1 : i, Pc.nw[0], Pc.nw[1], Pc.nw[2],
+                  &prep[nbuf][sc], &s_exh);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");                    // P(j)
+        scn = s_scn2[jb];
+        accepted = scn != 0;
+      } else {
+        const int t4 = tid - 128;                                         // 0..127
+        asm volatile("bar.sync 2, 160;" ::: "memory");                    // GO(j)
+        accepted = s_accept2[jb];
+        scn = 0;
+        if (accepted) {
+          const cplx* Mi = Minv2[jb];
+          const cplx* Dl = Dl2[jb];
+          // (a) U = (Sw[:, site] - delta) M^-1 (32 x 4), V = Delta Sw[site, :] (4 x 32); UA / VB = the same for my rows / columns
+          //     = my slice of the new columns of A / rows of B
+          {
+            const int ww = t4 >> 2, k = t4 & 3;
+            cplx accU = cmake(0.0, 0.0), accV = accU;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              cplx g = Sw[ww * LU_SWLD + kk * 8 + j];
+              if (ww == kk * 8 + j) g.x -= 1.0;
+              cfma(accU, g, Mi[kk * 4 + k]);
+              cfma(accV, Dl[k * 4 + kk], Sw[(kk * 8 + j) * LU_SWLD + ww]);
+            }
+            Us[ww * 4 + k] = accU;
+            Vs[k * LU_W + ww] = accV;
+          }
+          for (int e = t4; e < 8 * rpt; e += 128) {
+            const int q = e % (4 * rpt), rl = q >> 2, k = q & 3;
+            cplx acc = cmake(0.0, 0.0);
+            if (e < 4 * rpt) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                cplx g = GC[rl * LU_SWLD + kk * 8 + j];
+                if (row0 + rl == i + kk * N) g.x -= 1.0;
+                cfma(acc, g, Mi[kk * 4 + k]);
+              }
+              if (rl >= nown) acc = cmake(0.0, 0.0);
+              UAs[rl * 4 + k] = acc;
+              Aown[rl * ldo + np + k] = acc;
+              if (rl < nown) st_pub(Atw + (size_t)(row0 + rl) * ldk + np + k, acc);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) cfma(acc, Dl[k * 4 + kk], GR[(kk * 8 + j) * grld + rl]);
+              if (rl >= nown) acc = cmake(0.0, 0.0);
+              VBs[k * rpt + rl] = acc;
+              Bown[rl * ldo + np + k] = acc;
+              if (rl < nown) st_pub(Bmw + (size_t)(row0 + rl) * ldk + np + k, acc);
+            }
+          }
+          if (j + 1 < nb) {
+            asm volatile("bar.sync 4, 128;" ::: "memory");                // UPD: U, V, UA, VB complete
+            // (b) the whole window follows the update exactly: Sw += U V, GC += UA V, GR += U VB, one DMMA k-step (k = 4) per tile
+            const int rt = rpt >> 3;
+            const int nsw = sym ? 8 : 16, ngc = rt * 4, ntl = nsw + 2 * ngc;
+            const int r = lane >> 2, kq = lane & 3, c2 = 2 * kq;
+            for (int t = warp - 4; t < ntl; t += 4) {
+              const cplx* X; const cplx* Y; cplx* D; int ldy, ldd; bool mirror = false;
+              if (t < nsw) { const int tm = t >> 2, tnn = t & 3; X = Us + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = Sw + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; mirror = sym; }
+              else if (t < nsw + ngc) { const int qq = t - nsw, tm = qq >> 2, tnn = qq & 3; X = UAs + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = GC + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; }
+              else { const int qq = t - nsw - ngc, tm = qq & 3, tnn = qq >> 2; X = Us + tm * 8 * 4; Y = VBs + tnn * 8; ldy = rpt; D = GR + tm * 8 * grld + tnn * 8; ldd = grld; }
+              const cplx x = X[r * 4 + kq], y = Y[kq * ldy + r];
+              cplx* q0 = D + r * ldd + c2;
+              cplx v0 = q0[0], v1 = q0[1];
+              dmma884(v0.x, v1.x, x.x, y.x);
+              dmma884(v0.y, v1.y, x.x, y.y);
+              dmma884(v0.x, v1.x, -x.y, y.y);
+              dmma884(v0.y, v1.y, x.y, y.x);
+              q0[0] = v0; q0[1] = v1;
+              if (mirror) {   // t < 8: window rows tm*8 + r < 16
+                const int ww = (t >> 2) * 8 + r, wc = (t & 3) * 8 + c2;        // wc, wc + 1 lie in the same half
+                const bool left = wc < 16;
+                cplx* m0 = Sw + (ww + 16) * LU_SWLD + (left ? wc + 16 : wc - 16);
+                m0[0] = left ? cmake(v0.x, -v0.y) : cmake(-v0.x, v0.y);
+                m0[1] = left ? cmake(v1.x, -v1.y) : cmake(-v1.x, v1.y);
+              }
+            }
+          }
+        }
+        asm volatile("bar.arrive 3, 160;" ::: "memory");                  // DONE(j)
       }
-      if (fabs(det.y) > 1e-4 * fabs(det.x)) nonreal++;
-    } else if (warp <= 3) {
-      if (have_next) {
-        const int sc = warp - 1;                                  // 0 rejected, 1 accepted (no draw), 2 accepted (draw)
-        const Prep& Pc = prep[b][s_cur];
-        do_prep(a, fs, tn, nbr, uw, off + (sc == 1 ? 3 : 4), navail, i + 1, sc == 0 ? -1 : i, Pc.nw[0], Pc.nw[1], Pc.nw[2],
-                &prep[nbuf][sc], &s_exh);
-      }
+      // bookkeeping every role keeps for itself
+      if (accepted) { kc++; np += 4; }
+      if (warp <= 3) { off += (scn == 1) ? 3 : 4; s_cur = scn; }
     }
+    if (warp == 0) asm volatile("bar.sync 3, 160;" ::: "memory");          // DONE(nb-1)
     __syncthreads();
-    const int accepted = s_accept, scn = s_scn;
-    off += (scn == 1) ? 3 : 4;
-    long long ts1 = PROF ? clock64() : 0;
-    // ================= stage 2: accepted -> exact rank-4 update of the rest of the window; append / publish my slice of A, B =================
-    if (accepted) {
-      const Prep& P = prep[b][s_cur];
-      if (tid < 3) {
-        fs[3 * i + tid] = P.nw[tid];
-        if (blockIdx.x == 0) a.hs[(size_t)3 * N * sl + 3 * i + tid] = P.nw[tid];
-      }
-      // (a) U = (Sw[:, site] - delta) M^-1 (32 x 4), V = Delta Sw[site, :] (4 x 32); the same for my rows / columns:
-      //     UA = (GC[:, site] - delta) M^-1 = my rows of the new columns of A, VB = Delta GR[site, :] = my columns of the new rows of B
-      {
-        const int q = tid & 127, ww = q >> 2, k = q & 3;
-        cplx acc = cmake(0.0, 0.0);
-        if (tid < 128) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            cplx g = Sw[ww * LU_SWLD + kk * 8 + j];
-            if (ww == kk * 8 + j) g.x -= 1.0;
-            cfma(acc, g, Minv[kk * 4 + k]);
-          }
-          Us[ww * 4 + k] = acc;
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[k * 4 + kk], Sw[(kk * 8 + j) * LU_SWLD + ww]);
-          Vs[k * LU_W + ww] = acc;
-        }
-      }
-      if (tid < 8 * rpt) {
-        const int q = tid % (4 * rpt), rl = q >> 2, k = q & 3;
-        cplx acc = cmake(0.0, 0.0);
-        if (tid < 4 * rpt) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            cplx g = GC[rl * LU_SWLD + kk * 8 + j];
-            if (row0 + rl == i + kk * N) g.x -= 1.0;
-            cfma(acc, g, Minv[kk * 4 + k]);
-          }
-          if (rl >= nown) acc = cmake(0.0, 0.0);
-          UAs[rl * 4 + k] = acc;
-          Aown[rl * ldo + np + k] = acc;
-          if (rl < nown) st_pub(Atw + (size_t)(row0 + rl) * ldk + np + k, acc);
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) cfma(acc, P.D[k * 4 + kk], GR[(kk * 8 + j) * grld + rl]);
-          if (rl >= nown) acc = cmake(0.0, 0.0);
-          VBs[k * rpt + rl] = acc;
-          Bown[rl * ldo + np + k] = acc;
-          if (rl < nown) st_pub(Bmw + (size_t)(row0 + rl) * ldk + np + k, acc);
-        }
-      }
-      __syncthreads();
-      // (b) the whole window follows the update exactly: Sw += U V, GC += UA V, GR += U VB, one DMMA k-step (k = 4) per 8 x 8 tile
-      if (j + 1 < nb) {
-        const int rt = rpt >> 3;
-        const int nsw = sym ? 8 : 16, ngc = rt * 4, ntl = nsw + 2 * ngc;
-        const int r = lane >> 2, kq = lane & 3, c2 = 2 * kq;
-        for (int t = warp; t < ntl; t += 8) {
-          const cplx* X; const cplx* Y; cplx* D; int ldy, ldd; bool mirror = false;
-          if (t < nsw) { const int tm = t >> 2, tnn = t & 3; X = Us + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = Sw + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; mirror = sym; }
-          else if (t < nsw + ngc) { const int qq = t - nsw, tm = qq >> 2, tnn = qq & 3; X = UAs + tm * 8 * 4; Y = Vs + tnn * 8; ldy = LU_W; D = GC + tm * 8 * LU_SWLD + tnn * 8; ldd = LU_SWLD; }
-          else { const int qq = t - nsw - ngc, tm = qq & 3, tnn = qq >> 2; X = Us + tm * 8 * 4; Y = VBs + tnn * 8; ldy = rpt; D = GR + tm * 8 * grld + tnn * 8; ldd = grld; }
-          const cplx x = X[r * 4 + kq], y = Y[kq * ldy + r];
-          cplx* q0 = D + r * ldd + c2;
-          cplx v0 = q0[0], v1 = q0[1];
-          dmma884(v0.x, v1.x, x.x, y.x);
-          dmma884(v0.y, v1.y, x.x, y.y);
-          dmma884(v0.x, v1.x, -x.y, y.y);
-          dmma884(v0.y, v1.y, x.y, y.x);
-          q0[0] = v0; q0[1] = v1;
-          if (mirror) {   // t < 8: window rows tm*8 + r < 16
-            const int ww = (t >> 2) * 8 + r, wc = (t & 3) * 8 + c2;        // wc, wc + 1 lie in the same half
-            const bool left = wc < 16;
-            cplx* m0 = Sw + (ww + 16) * LU_SWLD + (left ? wc + 16 : wc - 16);
-            m0[0] = left ? cmake(v0.x, -v0.y) : cmake(-v0.x, v0.y);
-            m0[1] = left ? cmake(v1.x, -v1.y) : cmake(-v1.x, v1.y);
-          }
-        }
-      }
-      kc++;
-      np += 4;
-    }
     long long ts2 = PROF ? clock64() : 0;
+    const int i = s0 + nb - 1;                                             // last site of the block
     // ================= flush at a block end: G += A B over the pending 4*kc columns =================
-    const bool block_end = (j == nb - 1);
-    const bool do_flush = block_end && kc > 0 && (kc > kmax || i == N - 1);
+    const bool do_flush = kc > 0 && (kc > kmax || i == N - 1);
     if (do_flush) {
+      long long tf[6] = {0, 0, 0, 0, 0, 0};
+      if (PROF) tf[0] = clock64();
       bar_target += gridDim.x; grid_barrier_mono(bar_ctr, bar_target);     // also orders every thread's stage-2 smem traffic before the staging reuse
+      if (PROF) tf[1] = clock64();
       const cplx* Atb = Atw;
       const cplx* Bmb = Bmw;
       const int K = 4 * kc;
@@ -485,6 +540,7 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
           }
         }
         __syncthreads();                                   // staging ring free for the next tile's loads
+        if (PROF) tf[2] = clock64();
         cplx gv[4][2][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -513,29 +569,31 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
               }
             }
       }
+      if (PROF) tf[3] = clock64();
       bar_target += gridDim.x; grid_barrier_mono(bar_ctr, bar_target);
-      {   // re-arm my rows of the buffer just consumed (nobody reads it again before the flush after next)
+      if (PROF) tf[4] = clock64();
+      {   // re-arm my rows of the buffer just consumed (nobody reads it again before the flush after next): thread = (row, 32 threads per row)
         cplx* Atr = a.At + batch * bufstride;
         cplx* Bmr = a.Bm + batch * bufstride;
-        for (int e = tid; e < nown * K; e += blockDim.x) {
-          const int rl = e / K, p = e - rl * K;
-          st_sent(Atr + (size_t)(row0 + rl) * ldk + p);
-          st_sent(Bmr + (size_t)(row0 + rl) * ldk + p);
-        }
+        for (int rl = warp; rl < nown; rl += 8)
+          for (int p = lane; p < K; p += 32) {
+            st_sent(Atr + (size_t)(row0 + rl) * ldk + p);
+            st_sent(Bmr + (size_t)(row0 + rl) * ldk + p);
+          }
       }
+      if (PROF) { tf[5] = clock64(); for (int q = 0; q < 5; ++q) pf[q] += tf[q + 1] - tf[q]; }
       batch ^= 1;
       kc = 0;
       np = 0;
       if (PROF) pr[5]++;
     }
-    s_cur = scn;
-    __syncthreads();
-    if (PROF) { const long long ts3 = clock64(); pr[2] += ts1 - ts0; pr[3] += ts2 - ts1; pr[4] += ts3 - ts2; }
+    if (PROF) { const long long ts3 = clock64(); pr[2] += ts2 - ts0; pr[4] += ts3 - ts2; }
   }
   if (PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0) {
-    // [0] total, [1] gather, [2] form, [3] stage 1, [4] stage 2, [5] flush (+ end-of-iteration barrier), [6] #flushes, [7] accepts
+    // [0] total, [1] gather, [2] form, [3] site loops of the blocks, [4] -, [5] flush, [6] #flushes, [7] accepts
     a.prof[0] = clock64() - t_begin; a.prof[1] = pr[0]; a.prof[2] = pr[1]; a.prof[3] = pr[2]; a.prof[4] = pr[3]; a.prof[5] = pr[4];
     a.prof[6] = pr[5]; a.prof[7] = nacc;
+    for (int q = 0; q < 5; ++q) a.prof[8 + q] = pf[q];
   }
 
   if (blockIdx.x == 0 && tid == 0) {

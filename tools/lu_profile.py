@@ -21,8 +21,10 @@ if _os.environ.get("DQMC_LU_KERNEL") == "site":
     print(f" [site kernel] cycles total {tot}  stage1 {p[1]} ({p[1]/tot:.0%})  stage2(acc) {p[2]} ({p[2]/tot:.0%})  stage2(rej) {p[6]} ({p[6]/tot:.0%})  flush iters {p[3]} ({p[3]/tot:.0%})  flushes {p[4]} accepts {p[5]}")
 else:
     tot = p[0]; nblk = (N + 7) // 8
-    names = ("gather", "form", "stage1", "stage2", "flush+sync")
+    names = ("gather", "form", "site loops", "-", "flush")
     print(" [block kernel] cycles total %d: " % tot + "  ".join(f"{nm} {p[1+k]} ({p[1+k]/tot:.0%})" for k, nm in enumerate(names)) + f"  flushes {p[6]} accepts {p[7]}")
-    print(" per block: gather %.0f, form %.0f; per site: stage1 %.0f; per accept: stage2 %.0f; per flush: %.0f cycles" %
-          (p[1]/nblk, p[2]/nblk, p[3]/N, p[4]/max(p[7],1), p[5]/max(p[6],1)))
+    print(" per block: gather %.0f, form %.0f; per site: %.0f; per flush: %.0f cycles" %
+          (p[1]/nblk, p[2]/nblk, p[3]/N, p[5]/max(p[6],1)))
+    nf = max(p[6], 1)
+    print(" per flush: barrier-1 %.0f, staging+DMMA %.0f, G read-modify-write %.0f, barrier-2 %.0f, re-arm %.0f" % tuple(p[8+k]/nf for k in range(5)))
 mc.close()
