@@ -135,6 +135,25 @@ DQMC_D void grid_barrier(unsigned int* bar, unsigned int nblocks) {
 // Same, with a monotonic arrival counter and no generation word: CTA k-th barrier of a launch waits for the counter to reach
 // k * nblocks, so the release is the last arrival's atomic itself (one L2 round trip less than the count + generation scheme).
 // The counter must be zero at launch (the local-update kernel alternates between two counters and clears the idle one).
+// The same barrier in two halves, for work that may run between a CTA's arrival and the release (it must neither read what
+// other CTAs write before the barrier nor be needed by them): arrive = everything this CTA wrote so far is published.
+DQMC_D void grid_barrier_mono_arrive(unsigned int* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+DQMC_D void grid_barrier_mono_wait(unsigned int* ctr, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
 DQMC_D void grid_barrier_mono(unsigned int* ctr, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -21,11 +21,22 @@ __device__ __forceinline__ cplx ld_valid(const cplx* p) {
   } while (x == LU_SENT || y == LU_SENT);
   return make_double2(__longlong_as_double((long long)x), __longlong_as_double((long long)y));
 }
+// Publishing store of one element of the update factors.  LU_WEAK_PUB: a plain 16-byte store to L2 (one transaction, so a reader
+// sees the sentinel or the value); consumers spin on the data, so no ordering is needed -- and a CTA barrier that follows does not
+// have to wait for a strong (volatile) store to be acknowledged by L2.
 __device__ __forceinline__ void st_pub(cplx* p, cplx v) {
+#ifdef LU_WEAK_PUB
+  asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
   asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#endif
 }
 __device__ __forceinline__ void st_sent(cplx* p) {
+#ifdef LU_WEAK_PUB
+  asm volatile("st.global.cg.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(LU_SENT) : "memory");
+#else
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(LU_SENT) : "memory");
+#endif
 }
 // L2 load issued in program order relative to the other volatile asm statements (no memory clobber: ordinary accesses may move)
 __device__ __forceinline__ cplx ld_cg_issue(const cplx* p) {
@@ -130,8 +141,18 @@ __device__ __forceinline__ void do_prep(const LUArgs& a, const double* fs, const
   // interaction_matrix_exp_op!: old value with power -1, new value with power +1;  sinh(x)/|phi| = lam*dtau * sinh(x)/x
   const double l2 = a.lam_dtau * a.lam_dtau;
   double C1, q1, C2, q2;
+#ifdef LU_PREP_SPLIT_LANES
+  {   // lanes 0-15 evaluate the series for the old value, lanes 16-31 for the new one; one exchange instead of a second pass
+    double Cm, qm;
+    cosh_sinhc(l2 * (lane < 16 ? osq : nsq), &Cm, &qm);
+    const double Co = __shfl_xor_sync(0xffffffffu, Cm, 16), qo = __shfl_xor_sync(0xffffffffu, qm, 16);
+    C1 = lane < 16 ? Cm : Co; q1 = lane < 16 ? qm : qo;
+    C2 = lane < 16 ? Co : Cm; q2 = lane < 16 ? qo : qm;
+  }
+#else
   cosh_sinhc(l2 * osq, &C1, &q1);
   cosh_sinhc(l2 * nsq, &C2, &q2);
+#endif
   const double sh1 = -a.lam_dtau * q1, sh2 = a.lam_dtau * q2;
   const cplx S1 = cmake(-o1 * sh1, o2 * sh1), S2 = cmake(-n1 * sh2, n2 * sh2);
   const double R1 = -o3 * sh1, R2 = -n3 * sh2;
