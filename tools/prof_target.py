@@ -18,5 +18,11 @@ mc.set_uniforms(rs.rand(4 * L * L * M))
 for _ in range(5):
     mc.propagate()
 for w in which:
+    if w == 99:      # the column-pivoted QR of dqmc_decompose_udt (TDGF chains)
+        n = mc.n
+        X = (rs.rand(n, n) + 1j * rs.rand(n, n) - (0.5 + 0.5j)) * np.logspace(10, -30, n)[None, :]
+        mc.decompose_udt(X)
+        print(w, "qrcp")
+        continue
     print(w, mc.bench_kernel(w, 1))
 mc.close()
