@@ -331,15 +331,12 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
             Minv2[jb][r * 4 + c] = minv;
             Dl2[jb][lane] = P.D[lane];
           }
-          if (lane < 3) {
-            fs[3 * i + lane] = P.nw[lane];
-            if (blockIdx.x == 0) a.hs[(size_t)3 * N * sl + 3 * i + lane] = P.nw[lane];
-          }
           nacc++;
           dS_sum += P.mlog;
         }
         if (fabs(det.y) > 1e-4 * fabs(det.x)) nonreal++;
         __syncwarp();
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         if (j > 0) asm volatile("bar.sync 3, 160;" ::: "memory");        // DONE(j-1): the window is exact up to site j-1
         // what the block of site j+1 needs from the window, read BEFORE the update of site j may start
         cplx blk = cmake(0.0, 0.0), x1 = blk, x2 = blk;
@@ -348,6 +345,7 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
           x1 = Sw[(r * 8 + j + 1) * LU_SWLD + c * 8 + j];                 // X1[r][kk = c] = G_eff[row r of site j+1, col kk of site j]
           x2 = Sw[(r * 8 + j) * LU_SWLD + c * 8 + j + 1];                 // X2[kk = r][c] = G_eff[row kk of site j, col c of site j+1]
         }
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         asm volatile("bar.arrive 2, 160;" ::: "memory");                  // GO(j)
         if (j + 1 < nb) {
           if (accepted) {   // g4(j+1) = blk + (X1 M^-1)(Delta X2)
@@ -372,7 +370,15 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
           }
           if (lane < 16) g4s[lane] = blk;
         }
+        const double nw_mine = lane < 3 ? P.nw[lane] : 0.0;                // read before P(j): the proposal warps reuse prep[b] after it
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         asm volatile("bar.sync 1, 128;" ::: "memory");                    // P(j)
+        // the accepted value becomes the field only now: the proposals of site i+1 (which may still load fs[3i..] for the rejected
+        // scenario) are complete, and site i is no neighbour of site i+2 whose proposals start here
+        if (accepted && lane < 3) {
+          fs[3 * i + lane] = nw_mine;
+          if (blockIdx.x == 0) a.hs[(size_t)3 * N * sl + 3 * i + lane] = nw_mine;
+        }
       } else if (warp <= 3) {
         if (have_next) {
           const int sc = warp - 1;                                  // 0 rejected, 1 accepted (no draw), 2 accepted (draw)
@@ -380,11 +386,13 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
           do_prep(a, fs, tn, nbr, uw, off + (sc == 1 ? 3 : 4), navail, i + 1, sc == 0 ? -1 : i, Pc.nw[0], Pc.nw[1], Pc.nw[2],
                   &prep[nbuf][sc], &s_exh);
         }
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         asm volatile("bar.sync 1, 128;" ::: "memory");                    // P(j)
         scn = s_scn2[jb];
         accepted = scn != 0;
       } else {
         const int t4 = tid - 128;                                         // 0..127
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         asm volatile("bar.sync 2, 160;" ::: "memory");                    // GO(j)
         accepted = s_accept2[jb];
         scn = 0;
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
             }
           }
           if (j + 1 < nb) {
+            __syncwarp();   // named barriers are .aligned: the whole warp executes them together
             asm volatile("bar.sync 4, 128;" ::: "memory");                // UPD: U, V, UA, VB complete
             // (b) the whole window follows the update exactly: Sw += U V, GC += UA V, GR += U VB, one DMMA k-step (k = 4) per tile
             const int rt = rpt >> 3;
@@ -458,12 +467,14 @@ __global__ void __launch_bounds__(256) lu_block_kernel(LUArgs a) {
             }
           }
         }
+        __syncwarp();   // named barriers are .aligned: the whole warp executes them together
         asm volatile("bar.arrive 3, 160;" ::: "memory");                  // DONE(j)
       }
       // bookkeeping every role keeps for itself
       if (accepted) { kc++; np += 4; }
       if (warp <= 3) { off += (scn == 1) ? 3 : 4; s_cur = scn; }
     }
+    __syncwarp();   // named barriers are .aligned: the whole warp executes them together
     if (warp == 0) asm volatile("bar.sync 3, 160;" ::: "memory");          // DONE(nb-1)
     __syncthreads();
     long long ts2 = PROF ? clock64() : 0;

@@ -482,6 +482,9 @@ larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __r
   const int rbeg = min(m, rank * rchunk), rend = min(m, rbeg + rchunk);
 
   for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) Tsm[e % QR_NB][e / QR_NB] = T[e];
+  // split cluster barrier: "I am running" now, waited for right before the first store into another CTA's shared memory (a remote
+  // store is only defined once its target CTA has started; the wait is free, phase 1 lies in between)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
   // ---- phase 1: partial W = V^H C over my rows (32 x 8); 8-row steps dealt to the warps
   double cr[4][2], ci[4][2];
@@ -533,6 +536,7 @@ larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __r
 #pragma unroll
     for (int w = 0; w < 4; ++w) { sr += Wp[w][it][ln][e]; si += Wp[w][it][ln][2 + e]; }
     const cplx v = cmake(sr, si);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started
 #pragma unroll
     for (int dst = 0; dst < LC_CL; ++dst) {
       cplx* rs = cl.map_shared_rank(slots, dst);

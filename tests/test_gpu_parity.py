@@ -444,3 +444,28 @@ def test_wrap_greens_rejects_out_of_range_slices():
     mc.wrap_greens(g, 10, 1)
     mc.wrap_greens(g, 2, -1)
     mc.close()
+
+
+def test_input_validation_errors():
+    # (a) a uniform stream that could run dry is refused BEFORE the kernel touches G or the field (round-1 advisor finding);
+    # (b) measure_tdgfs! needs slices/2 to be a multiple of safe_mult (fill_tdgf! starts from the stabilized slice at beta/2)
+    from dqmc_b200 import DQMC, Params, UniformStream
+    from dqmc_b200.lib import DqmcError
+    L, M = 4, 10
+    mc, _ = _mk(L, M, False)
+    rs = np.random.RandomState(5)
+    mc.init(rs.rand(3, L * L, M))
+    g0, h0 = mc.greens, mc.hsfield
+    import ctypes as C
+    from dqmc_b200 import lib as _l
+    u = np.ascontiguousarray(rs.rand(4 * L * L - 1))
+    consumed, accepted, dS = C.c_int64(), C.c_int64(), C.c_double()
+    rc = mc.lib.dqmc_local_updates(mc._ctx, 0.5, _l.dptr(u), len(u), C.byref(consumed), C.byref(accepted), C.byref(dS))
+    assert rc != 0 and b"uniform stream exhausted" in mc.lib.dqmc_last_error(mc._ctx)
+    assert np.array_equal(mc.greens, g0) and np.array_equal(mc.hsfield, h0)
+    mc.close()
+    mc = DQMC(Params(L=4, slices=50, safe_mult=10, Bfield=False), device=0)
+    mc.init(rs.rand(3, 16, 50))
+    with pytest.raises(DqmcError, match="multiple of safe_mult"):
+        mc.measure_tdgfs()
+    mc.close()
