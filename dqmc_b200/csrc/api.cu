@@ -235,9 +235,11 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   c->lu_grid = local_updates_grid(c->n, c->num_sms, &c->lu_rpc);
   {   // the batch depth is halved until the kernel's shared memory fits (large lattices)
     const char* e = getenv("DQMC_LU_KERNEL");
-    c->lu_blk = c->lu_rpc <= 16 && !(e && strcmp(e, "site") == 0);
+    // block kernel: at most 16 rows per CTA, and L >= 4 (it writes an accepted value into the field while the proposals of the
+    // site after next are being evaluated: site i must not be a neighbour of site i+2)
+    c->lu_blk = c->lu_rpc <= 16 && c->p.L >= 4 && !(e && strcmp(e, "site") == 0);
     LUArgs probe; probe.nsites = c->N; probe.rpc = c->lu_rpc;
-    for (probe.kmax = c->kmax; probe.kmax > 2 && (c->lu_blk ? lu_block_smem(probe) : local_updates_smem(probe)) > (size_t)210 * 1024; probe.kmax /= 2) { }
+    for (probe.kmax = c->kmax; probe.kmax > 2 && (c->lu_blk ? lu_block_smem(probe) : local_updates_smem(probe)) > (size_t)(c->lu_blk ? 221 : 210) * 1024; probe.kmax /= 2) { }
     c->kmax = probe.kmax;
   }
   CU(c, cudaStreamSynchronize(c->st));
