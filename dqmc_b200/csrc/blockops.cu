@@ -5,6 +5,36 @@ __device__ __forceinline__ void cp_async_16(cplx* smem_dst, const cplx* gmem_src
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP): a column of the column-major matrix is one contiguous run of n x 16 bytes, so the
+// COLS pass moves its panel with one bulk copy per column in each direction (completion on an mbarrier for the loads, a bulk
+// group for the stores) instead of n/256 16-byte cp.async per thread and column.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "BLK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni BLK_DONE;\n"
+      "bra.uni BLK_WAIT;\n"
+      "BLK_DONE:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(gmem_dst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+}
+
 // One CTA stages `nvec` vectors of length n (columns for COLS, rows for ROWS) in shared memory,
 // applies every step of the chain in place, and writes them back.
 template <bool ROWS>
@@ -23,10 +53,16 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
   const int nvec = min(nvec_cta, n - v0);
   const int tid = threadIdx.x;
 
-  // ---- global -> shared: 16-byte cp.async copies, all in flight at once (no register round trip, no per-load stall)
+  // ---- global -> shared.  COLS: one TMA bulk copy per column; ROWS: 16-byte cp.async copies, all in flight at once
+  __shared__ __align__(8) unsigned long long ld_bar;
   if (!ROWS) {
-    for (int v = 0; v < nvec; ++v)
-      for (int j = tid; j < n; j += blockDim.x) cp_async_16(x + (size_t)v * ldx + j, mat + (size_t)(v0 + v) * ld + j);
+    if (tid == 0) mbar_init(&ld_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&ld_bar, (unsigned)(nvec * n * sizeof(cplx)));
+      for (int v = 0; v < nvec; ++v) bulk_g2s(x + (size_t)v * ldx, mat + (size_t)(v0 + v) * ld, (unsigned)(n * sizeof(cplx)), &ld_bar);
+    }
+    mbar_wait(&ld_bar, 0);
   } else {
     // element (row v0+v, col j): v fastest so that each column contributes nvec*16 contiguous bytes
     const int tot = nvec * n;
@@ -135,7 +171,17 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
   }
 
   // ---- shared -> global (optionally scale columns and emit their squared norms)
-  if (!ROWS) {
+  if (!ROWS && colscale == nullptr && colnorm2 == nullptr) {
+    // plain write-back: TMA bulk stores straight from the panel (the generic-proxy writes of the last step must be made visible
+    // to the async proxy first)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      for (int v = 0; v < nvec; ++v) bulk_s2g(mat + (size_t)(v0 + v) * ld, x + (size_t)v * ldx, (unsigned)(n * sizeof(cplx)));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (!ROWS) {
     for (int v = 0; v < nvec; ++v) {
       const double sc = colscale ? colscale[v0 + v] : 1.0;
       double acc = 0.0;

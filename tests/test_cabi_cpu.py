@@ -132,3 +132,23 @@ def test_julia_binding_matches_header(built):
     assert opens == ends, (opens, ends)
     for fn in ("initialize_stack", "build_stack", "propagate", "local_updates", "global_update", "wrap_greens!"):
         assert re.search(rf"function {re.escape(fn)}\(mc::AbstractDQMC\{{CBAssaadB200\}}", src), fn
+
+
+def test_bench_reference_arm_contract():
+    # bench.py --impl reference: one JSON line on stdout with the contract's keys, on the smallest BASELINE config (seconds of CPU)
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "L4_beta5", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sweeps/sec" and d["unit"] == "sweeps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["config"]["workload"] == "L4_beta5"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works: another rank prints nothing and exits 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "L4_beta5", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
