@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "local_updates.cuh"
 #include "misc.cuh"
+#include "paired.cuh"
 #include "qr.cuh"
 #include "zgemm.cuh"
 
@@ -83,6 +84,7 @@ struct dqmc_ctx {
   // only while it is known to hold.  sym_model: every operator handed to dqmc_set_operator has it (checked on the host);
   // sym_G: the current G has it (true after every calculate_greens of a symmetric model, measured for caller-supplied G).
   bool sym_lu_opt, sym_greens_opt, sym_model, sym_G;
+  bool paired_opt;                  // half-matrix stabilization (paired Householder QR) for symmetric models (DQMC_PAIRED=0: off)
   double* d_sym;                    // [2] scratch of sym_violation
   HostCSC csc[DQMC_OP_COUNT];
   QuadOp fop[F_COUNT];
@@ -196,6 +198,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   { const char* e = getenv("DQMC_LU_SYM"); c->sym_lu_opt = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("DQMC_GREENS_SYM"); c->sym_greens_opt = e ? atoi(e) != 0 : true; }
   c->sym_model = false; c->sym_G = false;
+  { const char* e = getenv("DQMC_PAIRED"); c->paired_opt = e ? atoi(e) != 0 : true; }
   const size_t n = c->n, nn = n * n;
   TRY(c, dmalloc(c, &c->G, nn));
   TRY(c, dmalloc(c, &c->Gtmp, nn));
@@ -579,8 +582,27 @@ static int wrap_greens_dev(dqmc_ctx* c, cplx* g, int slice, int dir) {
 // ---------------------------------------------------------------------------------------------- UDT / greens
 // decompose_udt! (linalg.jl:20-39): X (in c->W[0], destroyed; column norms^2 in c->colnorm) -> U, D, T(W[2]).
 // Pivoting = one stable sort of the columns by norm, then unpivoted blocked Householder QR.
+static bool use_paired(const dqmc_ctx* c) { return c->paired_opt && c->sym_model && c->n % 32 == 0 && c->n >= 64; }
+
+// The same for a matrix with the antiunitary flavour symmetry (every matrix of the stabilization path of a symmetric model):
+// only the left-half columns are sorted and factored, by PAIRED Householder steps (qr.cu), n/2 sequential steps instead of n and
+// half the flops; U and T are rebuilt in full from their halves.  oracle/experiments/{quaternion_qr,paired_panel_spec}.py.
+static int udt_paired_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
+  const int n = c->n, h = n / 2;
+  cplx* AL = c->W[1];
+  cplx* QHL = c->W[1] + (size_t)n * h;
+  TRY(c, argsort_desc(c->st, c->colnorm, h, c->perm));
+  TRY(c, gather_interleave_cols(c->st, c->W[0], n, n, c->perm, AL, n, c->num_sms));
+  TRY(c, set_identity_lint(c->st, QHL, n, n, c->num_sms));
+  TRY(c, qr_factor_paired(c->st, AL, n, n, c->W[3], n, Dout, c->tfac, QHL, n, h, c->lookahead ? &c->qra : nullptr));
+  TRY(c, build_U_paired(c->st, QHL, n, n, Uout, n, c->num_sms));
+  TRY(c, build_T_paired(c->st, AL, n, n, Dout, c->perm, c->W[2], n, c->num_sms));
+  return 0;
+}
+
 static int udt_dev(dqmc_ctx* c, cplx* Uout, double* Dout) {
   const int n = c->n;
+  if (use_paired(c)) return udt_paired_dev(c, Uout, Dout);
   TRY(c, argsort_desc(c->st, c->colnorm, n, c->perm));
   TRY(c, gather_cols(c->st, c->W[0], n, n, c->perm, c->W[1], n, c->num_sms));
   // Q^H is accumulated on the second stream while the (latency-bound) panel chain runs: Q^H = H_k^H ... H_1^H 1 is the
@@ -631,6 +653,11 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
     }
   }
   TRY(c, c->udt_qrcp_sweep ? udt_qrcp_dev(c, uslab(c, dst), dslab(c, dst)) : udt_dev(c, uslab(c, dst), dslab(c, dst)));
+  if (!c->udt_qrcp_sweep && use_paired(c)) {     // T_dst = T_new T_src is symmetric: left half + mirror
+    TRY(c, zgemm(c->st, OP_N, OP_N, n, n / 2, n, ONE, c->W[2], n, tslab(c, src), n, ZERO, tslab(c, dst), n, c->num_sms));
+    TRY(c, mirror_right_half(c->st, tslab(c, dst), n, n, c->num_sms));
+    return 0;
+  }
   TRY(c, zgemm(c->st, OP_N, OP_N, n, n, n, ONE, c->W[2], n, tslab(c, src), n, ZERO, tslab(c, dst), n, c->num_sms));
   return 0;
 }
@@ -641,6 +668,23 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
 static int calculate_greens_dev(dqmc_ctx* c, bool allow_sym = true) {
   ScopedTimer t(c, TM_GREENS);
   const int n = c->n;
+  if (allow_sym && c->sym_greens_opt && use_paired(c)) {
+    // half-matrix evaluation (oracle/experiments/half_matrix_greens.py): every operand is symmetric, so the bracket, its
+    // right-hand side, the solution and G are formed as left halves (n x n/2) and mirrored; the bracket is factored by the paired QR
+    const int h = n / 2;
+    cplx *innerL = c->W[2], *rhsL = c->W[2] + (size_t)n * h;
+    TRY(c, zgemm(c->st, OP_C, OP_N, n, h, n, ONE, c->Ul, n, c->Ur, n, ZERO, c->W[0], n, c->num_sms));
+    TRY(c, zgemm(c->st, OP_N, OP_C, n, h, n, ONE, c->Tl, n, c->Tr, n, ZERO, c->W[1], n, c->num_sms));
+    TRY(c, loh_assemble_paired(c->st, n, c->W[0], c->W[1], c->Dl, c->Dr, c->Ul, innerL, rhsL, c->drp_inv, c->num_sms));
+    TRY(c, qr_factor_paired(c->st, innerL, n, n, c->W[3], n, c->dabs, c->tfac, rhsL, n, h, c->lookahead ? &c->qra : nullptr));
+    TRY(c, expand_R_paired(c->st, innerL, n, n, c->W[4], n, c->num_sms));
+    TRY(c, trsm_upper(c->st, c->W[4], n, n, rhsL, n, h, c->trsm_work, nullptr, c->num_sms, 1));
+    TRY(c, uninterleave_rows(c->st, rhsL, n, n, c->drp_inv, c->W[0], n, c->num_sms));
+    TRY(c, zgemm(c->st, OP_N, OP_N, n, h, n, ONE, c->Ur, n, c->W[0], n, ZERO, c->G, n, c->num_sms));
+    TRY(c, mirror_right_half(c->st, c->G, n, n, c->num_sms));
+    c->sym_G = true;
+    return 0;
+  }
   TRY(c, zgemm(c->st, OP_C, OP_N, n, n, n, ONE, c->Ul, n, c->Ur, n, ZERO, c->W[0], n, c->num_sms));
   TRY(c, zgemm(c->st, OP_N, OP_C, n, n, n, ONE, c->Tl, n, c->Tr, n, ZERO, c->W[1], n, c->num_sms));
   TRY(c, loh_assemble(c->st, n, c->W[0], c->W[1], c->Dl, c->Dr, c->Ul, c->W[2], c->W[3], c->drp_inv, c->num_sms));
@@ -1546,5 +1590,46 @@ extern "C" int dqmc_test_zgemm(dqmc_ctx* c, int opA, int opB, int M, int N, int 
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   if (rc) { memcpy(c->err, g_errbuf, sizeof(g_errbuf)); return -1; }
   if (e != cudaSuccess) CTX_FAIL(c, "dqmc_test_zgemm: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Test hooks of the half-matrix path.  dqmc_test_qr_paired: the paired QR on host data (n = the context's matrix size): XL and rhs
+// are n x n/2 with pair-interleaved rows; on return XL = R_L, rhs = Q^H rhs, V = the n x n explicit reflector blocks, Tfac = the
+// n/32 compact-WY factors (32 x 32 each), dabs = n moduli.  lookahead != 0 runs the two-stream driver.
+extern "C" int dqmc_test_qr_paired(dqmc_ctx* c, double* XL, double* rhs, double* V, double* Tfac, double* dabs, int32_t lookahead) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int n = c->n, h = n / 2;
+  const size_t half = sizeof(cplx) * (size_t)n * h;
+  CU(c, cudaMemcpyAsync(c->W[1], XL, half, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->W[1] + (size_t)n * h, rhs, half, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemsetAsync(c->W[3], 0, 2 * half, c->st));
+  TRY(c, qr_factor_paired(c->st, c->W[1], n, n, c->W[3], n, c->dabs, c->tfac, c->W[1] + (size_t)n * h, n, h, lookahead ? &c->qra : nullptr));
+  CU(c, cudaMemcpyAsync(XL, c->W[1], half, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(rhs, c->W[1] + (size_t)n * h, half, cudaMemcpyDeviceToHost, c->st));
+  if (V) CU(c, cudaMemcpyAsync(V, c->W[3], 2 * half, cudaMemcpyDeviceToHost, c->st));
+  if (Tfac) CU(c, cudaMemcpyAsync(Tfac, c->tfac, sizeof(cplx) * (size_t)(n / 32) * QR_NB * QR_NB, cudaMemcpyDeviceToHost, c->st));
+  if (dabs) CU(c, cudaMemcpyAsync(dabs, c->dabs, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// dqmc_test_udt: the sweep's decompose_udt! on a host matrix (sort-once QR, or the paired one if paired != 0; the caller
+// guarantees the symmetry then) -> U, D, T.
+extern "C" int dqmc_test_udt(dqmc_ctx* c, const double* x, double* U, double* D, double* T, int32_t paired) {
+  CU(c, cudaSetDevice(c->p.device));
+  const int n = c->n;
+  const size_t nn = sizeof(cplx) * (size_t)n * n;
+  if (paired && (n % 32 != 0 || n < 64)) CTX_FAIL(c, "dqmc_test_udt: the paired factorization needs n %% 32 == 0, n >= 64");
+  CU(c, cudaMemcpyAsync(c->W[0], x, nn, cudaMemcpyHostToDevice, c->st));
+  TRY(c, colnorm2(c->st, c->W[0], n, n, c->colnorm));
+  const bool po = c->paired_opt, smo = c->sym_model;
+  c->paired_opt = paired != 0; if (paired) c->sym_model = true;
+  const int rc = udt_dev(c, c->W[4], c->dabs);
+  c->paired_opt = po; c->sym_model = smo;
+  if (rc) { memcpy(c->err, g_errbuf, sizeof(g_errbuf)); return -1; }
+  CU(c, cudaMemcpyAsync(U, c->W[4], nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(T, c->W[2], nn, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(D, c->dabs, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
   return 0;
 }

@@ -312,18 +312,312 @@ qr_panel_kernel(cplx* __restrict__ A, int lda, int m, int nb, cplx* __restrict__
 }
 
 // =====================================================================================================
+// PAIRED panel factorization for matrices with the antiunitary flavour symmetry S = [[A, B], [-conj(B), conj(A)]]
+// (executable specification, formula by formula: oracle/experiments/paired_panel_spec.py).  The matrix is held as its LEFT
+// HALF with pair-interleaved rows (rows 2i, 2i+1 = natural rows i, i+n/2 = one quaternion); column c+n/2 is the partner
+// psi(x)[2i] = -conj(x[2i+1]), psi(x)[2i+1] = conj(x[2i]) of column c.  One pair-step eliminates a column AND its partner
+// with the two mutually orthogonal reflectors v, psi(v):  H = 1 - tau (v v^H + psi(v) psi(v)^H), real tau -- so a
+// factorization has n/2 sequential steps instead of n, each with the same exchange (one per step) and the same number of
+// multiply-adds as a step of qr_panel_kernel.  A panel = 16 pair-steps = 32 reflectors V = [v_0, psi(v_0), v_1, ...], written
+// out EXPLICITLY (m x 32, 2x2 blocks on the diagonal), so larfb_kernel / larfb_cluster_kernel apply it unchanged (vmode 1).
+// Thread (lane, warp g): column lane & 15, component lane >> 4 (0: even rows "e", 1: odd rows "o") on the quaternion rows
+// {g + 8 t} of the CTA's slab, in registers.  Raw dot products over the rows strictly below row pair j,
+//     D1_c = sum conj(x_e) c_e + conj(x_o) c_o,      D2_c = sum x_e c_o - x_o c_e,
+// are all a step needs besides row pair j of the panel; lanes c / c+16 end up with D1_c / D2_c of their column (one shuffle),
+// which is exactly the 32-slot exchange vector of the unpaired kernel.
+// =====================================================================================================
+#define QP_NP 16       // pair-steps per panel
+#define QP_TMAX 24     // quaternion rows per thread, upper bound
+struct PairedSmem {
+  cplx part[8][QR_NB];                // per-warp partial dots: slot c = D1_c, slot c+16 = D2_c
+  cplx colbuf[8][2][QP_TMAX];         // current column on the quaternion rows of warp g: [component][t] (zero on rows <= j)
+  cplx rowl[QR_NB];                   // row pair j of the panel (rank 0): slot c = e, slot c+16 = o
+  cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][slot]
+  cplx rowv[2][QR_NB];                // [parity][slot]: row pair j (pushed by rank 0)
+  cplx Tsm[QR_NB][QR_NB + 1];         // compact-WY T; rows {g, g+8, g+16, g+24} belong to warp g
+  cplx gsm[8][2][QR_NB];              // per warp: V^H v_j and V^H psi(v_j)
+  cplx udiag[QR_NB];                  // v_j on its own row pair: slot j = e, slot j+16 = o
+  double tau_s[QP_NP], nx_s[QP_NP];
+  unsigned long long full[2];
+};
+
+// one column of T (zlarft, forward / columnwise) by warp g for its rows i = g + 8q: T(i, col) = -tau sum_{k=i}^{col-1} T(i,k) gv(k)
+__device__ __forceinline__ void paired_t_column(PairedSmem& S, int g, int lane, int col, double tau, const cplx* gv) {
+  const int q = lane >> 3, hh = lane & 7, i = g + 8 * q;
+  cplx acc = cmake(0.0, 0.0);
+  if (i < col) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = hh + 8 * kk;
+      if (k >= i && k < col) cfma(acc, S.Tsm[i][k], gv[k]);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+  }
+  if (hh == 0) {
+    if (i < col) S.Tsm[i][col] = cmake(-tau * acc.x, -tau * acc.y);
+    else if (i == col) S.Tsm[i][i] = cmake(tau, 0.0);
+  }
+  __syncwarp();
+}
+
+template <int T, bool GENERAL>
+__device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
+                                                  cplx* __restrict__ Vout, int ldv, int m, int np, int r_begin, int nloc,
+                                                  double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout) {
+  constexpr int NW = 8;
+  constexpr bool KEEP = (T <= 10);               // current column kept in registers between the dot and the update phase
+  const int rank = (int)cl.block_rank();
+  const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
+  const int col = lane & 15, comp = lane >> 4;
+  const bool doT = (rank == panel_t_rank(m));
+  cplx x[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int rl = 2 * (g + NW * t) + comp;
+    x[t] = rl < nloc ? a[rl * QR_LDA + col] : cmake(0.0, 0.0);
+  }
+  if (col == 0) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) S.colbuf[g][comp][t] = (!GENERAL || g + NW * t > 0) ? x[t] : cmake(0.0, 0.0);
+  }
+  const uint32_t dst_rank = (uint32_t)g;         // warp g pushes to CTA g (NW == QR_CL)
+  const uint32_t r_xch = mapa_u32(smem_u32(&S.xch[0][rank][lane]), dst_rank);
+  const uint32_t r_row = mapa_u32(smem_u32(&S.rowv[0][lane]), dst_rank);
+  const uint32_t r_bar = mapa_u32(smem_u32(&S.full[0]), dst_rank);
+  const uint32_t l_bar = smem_u32(&S.full[0]);
+  cl.sync();   // every CTA's barriers are initialised before anybody stores into them
+
+  double tau_prev = 0.0;
+  double sc = 1.0;                               // 1/|x| of my column once it is finished (v = sc * u)
+  for (int j = 0; j < np; ++j) {
+    const int par = j & 1;
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar + 8 * par), "r"(QR_TX_BYTES) : "memory");
+    // ---- phase A: raw dots of the current column with my column over my rows (rows <= j are zero in the column buffer)
+    cplx dA[KEEP ? T : 1], dB[KEEP ? T : 1];
+    (void)dA; (void)dB;
+    {
+      cplx p1a = cmake(0.0, 0.0), p1b = p1a, p2a = p1a, p2b = p1a;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const cplx ca = S.colbuf[g][comp][t], cb = S.colbuf[g][comp ^ 1][t];
+        if constexpr (KEEP) { dA[t] = ca; dB[t] = cb; }
+        if (t & 1) { cfma_conj(p1b, ca, x[t]); cfma(p2b, cb, x[t]); }
+        else       { cfma_conj(p1a, ca, x[t]); cfma(p2a, cb, x[t]); }
+      }
+      cplx p1 = cadd(p1a, p1b), p2 = cadd(p2a, p2b);
+      if (comp == 0) p2 = cneg(p2);              // D2 = sum x_e c_o - x_o c_e: the e-lanes hold -(x_o c_e)
+      const cplx o1 = cmake(__shfl_xor_sync(0xffffffffu, p1.x, 16), __shfl_xor_sync(0xffffffffu, p1.y, 16));
+      const cplx o2 = cmake(__shfl_xor_sync(0xffffffffu, p2.x, 16), __shfl_xor_sync(0xffffffffu, p2.y, 16));
+      S.part[g][lane] = comp == 0 ? cadd(p1, o1) : cadd(p2, o2);
+      if (GENERAL) {
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (g + NW * t == j) S.rowl[lane] = (col < j) ? cscale(x[t], sc) : x[t];
+      }
+    }
+    __syncthreads();
+    {
+      // warp g sums the 8 partials of slot `lane` and pushes the result (and row pair j, if mine) to CTA g of the cluster
+      const cplx p0 = cadd(S.part[0][lane], S.part[1][lane]), p1 = cadd(S.part[2][lane], S.part[3][lane]);
+      const cplx p2 = cadd(S.part[4][lane], S.part[5][lane]), p3 = cadd(S.part[6][lane], S.part[7][lane]);
+      cplx tot = cadd(cadd(p0, p1), cadd(p2, p3));
+      if (col < j) tot = cscale(tot, sc);        // finished column: its rows are stored unscaled
+      st_async_c16(r_xch + par * (QR_CL * QR_NB * 16), tot, r_bar + 8 * par);
+      if (GENERAL) st_async_c16(r_row + par * (QR_NB * 16), S.rowl[lane], r_bar + 8 * par);
+    }
+    if (doT && j > 0) {
+      // the two T columns of the previous pair-step, in the shadow of the exchange
+      paired_t_column(S, g, lane, 2 * (j - 1), tau_prev, S.gsm[g][0]);
+      paired_t_column(S, g, lane, 2 * (j - 1) + 1, tau_prev, S.gsm[g][1]);
+    }
+    mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
+    // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
+    cplx tc;
+    double tj;
+    {
+      const cplx c0 = cadd(S.xch[par][0][lane], S.xch[par][1][lane]), c1 = cadd(S.xch[par][2][lane], S.xch[par][3][lane]);
+      const cplx c2 = cadd(S.xch[par][4][lane], S.xch[par][5][lane]), c3 = cadd(S.xch[par][6][lane], S.xch[par][7][lane]);
+      const double j0 = S.xch[par][0][j].x + S.xch[par][1][j].x, j1 = S.xch[par][2][j].x + S.xch[par][3][j].x;
+      const double j2 = S.xch[par][4][j].x + S.xch[par][5][j].x, j3 = S.xch[par][6][j].x + S.xch[par][7][j].x;
+      tc = cadd(cadd(c0, c1), cadd(c2, c3));
+      tj = (j0 + j1) + (j2 + j3);
+    }
+    const cplx tother = cmake(__shfl_xor_sync(0xffffffffu, tc.x, 16), __shfl_xor_sync(0xffffffffu, tc.y, 16));
+    const cplx D1 = comp == 0 ? tc : tother, D2 = comp == 0 ? tother : tc;
+    const cplx xe0 = S.rowv[par][j], xo0 = S.rowv[par][j + 16];
+    const cplx ce0 = S.rowv[par][col], co0 = S.rowv[par][col + 16];
+    const double q2 = cabs2(xe0) + cabs2(xo0);
+    const double nrm2 = q2 + tj;
+    double f = 0.0, rnj = 0.0, tau = 0.0, nx = 0.0;
+    cplx ue0 = cmake(0.0, 0.0), uo0 = ue0;
+    if (nrm2 > 0.0) {
+      nx = sqrt(nrm2);
+      const double q = sqrt(q2);
+      f = 1.0 / (nx * (nx + q));
+      if (q > 0.0) {
+        const double s1 = (q + nx) / q;
+        ue0 = cscale(xe0, s1); uo0 = cscale(xo0, s1);
+      } else {
+        ue0 = cmake(nx, 0.0);
+      }
+      rnj = (nx + q) * f;                        // 1 / |x|
+      tau = nx * nx * f;                         // |x| / (|x| + |x_j|)
+    }
+    // uc = u^H c = D1 + conj(ue0) ce0 + conj(uo0) co0,   pc = psi(u)^H c = D2 + ue0 co0 - uo0 ce0
+    cplx uc = D1, pc = D2;
+    cfma_conj(uc, ue0, ce0); cfma_conj(uc, uo0, co0);
+    cfma(pc, ue0, co0); cfma(pc, cneg(uo0), ce0);
+    if (doT && comp == 0) {
+      // Gram entries against the finished columns (their dots and row entries arrived scaled by 1/|x_c|)
+      const bool fin = col < j;
+      const cplx z = cmake(0.0, 0.0);
+      S.gsm[g][0][2 * col] = fin ? cmake(rnj * uc.x, -rnj * uc.y) : z;        // v_c^H v_j        =  conj(uc)
+      S.gsm[g][0][2 * col + 1] = fin ? cmake(-rnj * pc.x, -rnj * pc.y) : z;   // psi(v_c)^H v_j   = -pc
+      S.gsm[g][1][2 * col] = fin ? cmake(rnj * pc.x, -rnj * pc.y) : z;        // v_c^H psi(v_j)   =  conj(pc)
+      S.gsm[g][1][2 * col + 1] = fin ? cmake(rnj * uc.x, rnj * uc.y) : z;     // psi(v_c)^H psi(v_j) = uc
+    }
+    if (tid == 0) {
+      S.tau_s[j] = tau; S.nx_s[j] = nx;
+      S.udiag[j] = cscale(ue0, rnj); S.udiag[j + 16] = cscale(uo0, rnj);
+    }
+    tau_prev = tau;
+    // ---- phase D: c += A alpha + conj(B) beta on the rows below row pair j (A = my component of the current column,
+    // B = the other one), alpha = -f uc, beta = +-f pc (e / o lanes); row pair j itself with u_j (rank 0)
+    const bool upd = col > j;
+    const cplx alpha = upd ? cmake(-f * uc.x, -f * uc.y) : cmake(0.0, 0.0);
+    const double fb = comp == 0 ? f : -f;
+    const cplx beta = upd ? cmake(fb * pc.x, fb * pc.y) : cmake(0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      cplx ca, cb;
+      if constexpr (KEEP) { ca = dA[t]; cb = dB[t]; }
+      else { ca = S.colbuf[g][comp][t]; cb = S.colbuf[g][comp ^ 1][t]; }
+      cfma(x[t], ca, alpha);
+      cfma_conj(x[t], cb, beta);
+      if (GENERAL) {
+        if (g + NW * t == j && col >= j) {
+          const cplx myU = comp == 0 ? ue0 : uo0, otU = comp == 0 ? uo0 : ue0;
+          if (col == j) x[t] = comp == 0 ? csub(xe0, ue0) : csub(xo0, uo0);
+          else { cfma(x[t], myU, alpha); cfma_conj(x[t], otU, beta); }
+        }
+      }
+    }
+    if (col == j) sc = rnj;
+    if (!KEEP) __syncwarp();                     // everybody has re-read the column buffer before it is overwritten
+    if (col == j + 1) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) S.colbuf[g][comp][t] = (!GENERAL || g + NW * t > j + 1) ? x[t] : cmake(0.0, 0.0);
+    }
+    __syncwarp();
+  }
+  if (doT) {
+    paired_t_column(S, g, lane, 2 * (np - 1), tau_prev, S.gsm[g][0]);
+    paired_t_column(S, g, lane, 2 * (np - 1) + 1, tau_prev, S.gsm[g][1]);
+  }
+  __syncthreads();   // udiag / T complete; the staging area is free (nobody reads `a` after the initial load)
+  // ---- R: rows at or above the quaternion diagonal keep their values, eliminated entries are exact zeros
+  const int q_begin = r_begin >> 1;              // global quaternion row of my first local one (within the panel)
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int ql = g + NW * t, rl = 2 * ql + comp;
+    if (rl < nloc) a[rl * QR_LDA + col] = (q_begin + ql <= col) ? x[t] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int e = tid; e < nloc * QP_NP; e += NW * 32) {
+    const int rl = e % nloc, cc = e / nloc;
+    if (cc < np) A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
+  }
+  __syncthreads();
+  // ---- V = [v_0, psi(v_0), v_1, ...] explicit: column 2c = v_c, column 2c+1: rows (2q, 2q+1) = (-conj(v_o), conj(v_e))
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int ql = g + NW * t, rl = 2 * ql + comp;
+    if (rl < nloc) {
+      const int qg = q_begin + ql;
+      cplx v = cmake(0.0, 0.0);
+      if (col < np) {
+        if (qg > col) v = cscale(x[t], sc);
+        else if (qg == col) v = S.udiag[col + 16 * comp];
+      }
+      a[rl * QR_LDA + 2 * col] = v;
+      // my value feeds the OTHER row of the pair in the partner column
+      a[(rl ^ 1) * QR_LDA + 2 * col + 1] = comp == 0 ? cmake(v.x, -v.y) : cmake(-v.x, v.y);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nloc * QR_NB; e += NW * 32) {
+    const int rl = e % nloc, cc = e / nloc;
+    Vout[(size_t)cc * ldv + r_begin + rl] = a[rl * QR_LDA + cc];
+  }
+  if (doT) {
+    for (int e = tid; e < QR_NB * QR_NB; e += NW * 32) {
+      const int i = e % QR_NB, k = e / QR_NB;
+      Tout[e] = (i < 2 * np && k < 2 * np && i <= k) ? S.Tsm[i][k] : cmake(0.0, 0.0);
+    }
+    if (tid < np) { dabs_out[tid] = S.nx_s[tid]; if (dabs_dup) dabs_out[dabs_dup + tid] = S.nx_s[tid]; }
+  }
+  cl.sync();  // no CTA may exit while others may still write into its shared memory
+}
+
+// Row split of the paired panel: rank 0 owns the first 32 interleaved rows (16 quaternion rows, the diagonal block), the rest
+// is dealt to ranks 1..7 in whole quaternion rows.
+__host__ __device__ __forceinline__ int paired_rows_below(int m) { return 2 * ((max(0, m - QR_NB) / 2 + QR_CL - 2) / (QR_CL - 1)); }
+
+template <int T>
+__global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(256)
+qr_panel_paired_kernel(cplx* __restrict__ A, int lda, cplx* __restrict__ Vout, int ldv, int m, int np,
+                       double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
+  const int rs1 = paired_rows_below(m);
+  const int r_begin = rank == 0 ? 0 : min(m, QR_NB + (rank - 1) * rs1);
+  const int nloc = rank == 0 ? min(m, QR_NB) : max(0, min(m, r_begin + rs1) - r_begin);
+  const int tid = threadIdx.x;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // staging for the coalesced load / stores: a[rl*QR_LDA + c]
+  __shared__ __align__(16) PairedSmem S;
+
+  for (int e = tid; e < nloc * QP_NP; e += 256) {
+    const int rl = e % nloc, cc = e / nloc;
+    a[rl * QR_LDA + cc] = cc < np ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
+  }
+  if (rank == panel_t_rank(m))
+    for (int e = tid; e < QR_NB * (QR_NB + 1); e += 256) (&S.Tsm[0][0])[e] = cmake(0.0, 0.0);
+  if (tid < QR_NB) S.udiag[tid] = cmake(0.0, 0.0);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (rank == 0) panel_body_paired<2, true>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout);
+  else panel_body_paired<T, false>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout);
+}
+
+// =====================================================================================================
 // Block-reflector application  C <- (I - V op(T) V^H) C  on 8-column blocks of C, streaming V and C
 // from L2 in DMMA fragment order (no shared-memory staging of the operands).
 // =====================================================================================================
-__device__ __forceinline__ cplx vmask_load(const cplx* __restrict__ V, int ldv, int m, int r, int c) {
-  if (r >= m || r < c) return cmake(0.0, 0.0);
-  if (r == c) return cmake(1.0, 0.0);
+// vmode 0: V is stored LAPACK style in the factored panel (unit diagonal implied, R above it); vmode 1: V is an explicit
+// m x 32 block, zeros included (the paired panel kernel writes it that way: 2x2 blocks on its diagonal)
+__device__ __forceinline__ cplx vmask_load(const cplx* __restrict__ V, int ldv, int m, int r, int c, int vmode) {
+  if (r >= m) return cmake(0.0, 0.0);
+  if (!vmode) {
+    if (r < c) return cmake(0.0, 0.0);
+    if (r == c) return cmake(1.0, 0.0);
+  }
   return V[(size_t)c * ldv + r];
 }
 
 __global__ void __launch_bounds__(256)
 larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict__ T, int conjT,
-             cplx* __restrict__ C, int ldc, int ncols) {
+             cplx* __restrict__ C, int ldc, int ncols, int vmode) {
   __shared__ cplx Tsm[QR_NB][QR_NB + 1];
   __shared__ double Wp[4][4][32][4];
   __shared__ cplx W1[QR_NB][8], W2[QR_NB][8];
@@ -348,7 +642,7 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int c = it * 8 + lo;
-        av[u][it] = (r >= QR_NB && r < kend) ? V[(size_t)c * ldv + r] : (r < kend ? vmask_load(V, ldv, m, r, c) : cmake(0.0, 0.0));
+        av[u][it] = (r >= QR_NB && r < kend) ? V[(size_t)c * ldv + r] : (r < kend ? vmask_load(V, ldv, m, r, c, vmode) : cmake(0.0, 0.0));
       }
       bv[u] = (r < kend && colok) ? C[(size_t)(c0 + lo) * ldc + r] : cmake(0.0, 0.0);
     }
@@ -419,7 +713,7 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int c = kk * 4 + lk;
-      av[kk] = (rt * 8 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c);
+      av[kk] = (rt * 8 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c, vmode);
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -467,7 +761,7 @@ larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict_
 #define LC_CL 8
 __global__ void __cluster_dims__(LC_CL, 1, 1) __launch_bounds__(256)
 larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict__ T, int conjT,
-                     cplx* __restrict__ C, int ldc, int ncols) {
+                     cplx* __restrict__ C, int ldc, int ncols, int vmode) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* slots = reinterpret_cast<cplx*>(smem_raw);           // [LC_CL][256]: partial W of every CTA of the cluster
@@ -499,7 +793,7 @@ larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __r
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int c = it * 8 + lo;
-        av[u][it] = (r >= QR_NB && r < rend) ? V[(size_t)c * ldv + r] : (r < rend ? vmask_load(V, ldv, m, r, c) : cmake(0.0, 0.0));
+        av[u][it] = (r >= QR_NB && r < rend) ? V[(size_t)c * ldv + r] : (r < rend ? vmask_load(V, ldv, m, r, c, vmode) : cmake(0.0, 0.0));
       }
       bv[u] = (r < rend && colok) ? C[(size_t)(c0 + lo) * ldc + r] : cmake(0.0, 0.0);
     }
@@ -566,7 +860,7 @@ larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __r
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int c = kk * 4 + lk;
-      av[kk] = (r0 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c);
+      av[kk] = (r0 >= QR_NB && r < m) ? V[(size_t)c * ldv + r] : vmask_load(V, ldv, m, r, c, vmode);
     }
     double dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
 #pragma unroll
@@ -632,18 +926,18 @@ static int launch_panel(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* 
 
 int g_larfb_cluster_max_cols = 256;   // column count up to which the row-split cluster kernel is used
 static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cplx* T, int conjT, cplx* C, int ldc,
-                        int ncols) {
+                        int ncols, int vmode = 0) {
   if (ncols <= 0) return 0;
   if (ncols <= g_larfb_cluster_max_cols && m >= 64) {
     static SmemMemo memo;
     const size_t smem = sizeof(cplx) * LC_CL * 256;
     if (ensure_dynamic_smem(larfb_cluster_kernel, memo, smem)) return -1;
-    larfb_cluster_kernel<<<((ncols + 7) / 8) * LC_CL, 256, smem, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
+    larfb_cluster_kernel<<<((ncols + 7) / 8) * LC_CL, 256, smem, st>>>(V, ldv, m, T, conjT, C, ldc, ncols, vmode);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     return 0;
   }
-  larfb_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
+  larfb_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, C, ldc, ncols, vmode);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
@@ -701,6 +995,75 @@ int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, 
   return 0;
 }
 
+// ---- paired factorization: driver.  AL: n x n/2 (left half, pair-interleaved rows), factored in place into the quaternion
+// upper triangle R_L (exact zeros below); V: n x n scratch receiving the explicit reflector blocks (panel k at (32k, 32k));
+// dabs[0:n/2] (and a copy in dabs[n/2:n]) = quaternion modulus of the diagonal of R; rhs (n x nrhs, pair-interleaved rows) <- Q^H rhs.
+template <int T>
+static int launch_panel_paired_t(cudaStream_t st, cplx* A, int lda, cplx* V, int ldv, int m, int np, double* dabs, int dup,
+                                 cplx* Tf, size_t smem) {
+  static SmemMemo memo;
+  size_t smem_lim = 0;
+  if (ensure_max_dynamic_smem(qr_panel_paired_kernel<T>, memo, &smem_lim)) return -1;
+  if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "paired qr panel: m=%d too large", m); return -1; }
+  qr_panel_paired_kernel<T><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+static int launch_panel_paired(cudaStream_t st, cplx* A, int lda, cplx* V, int ldv, int m, int np, double* dabs, int dup, cplx* T) {
+  const int rs = paired_rows_below(m);            // interleaved rows per CTA below the diagonal block
+  const size_t smem = sizeof(cplx) * ((size_t)QR_LDA * max(rs, QR_NB) + 8);
+  const int tq = (rs / 2 + 7) / 8;                // quaternion rows per thread
+#define PP(TT) return launch_panel_paired_t<TT>(st, A, lda, V, ldv, m, np, dabs, dup, T, smem)
+  if (tq <= 1) PP(1);
+  if (tq <= 2) PP(2);
+  if (tq <= 3) PP(3);
+  if (tq <= 4) PP(4);
+  if (tq <= 5) PP(5);
+  if (tq <= 6) PP(6);
+  if (tq <= 7) PP(7);
+  if (tq <= 8) PP(8);
+  if (tq <= 9) PP(9);
+  if (tq <= 10) PP(10);
+  if (tq <= 12) PP(12);
+  if (tq <= 14) PP(14);
+  if (tq <= 16) PP(16);
+  if (tq <= 20) PP(20);
+#undef PP
+  snprintf(g_errbuf, sizeof(g_errbuf), "paired qr panel: m=%d too large", m);
+  return -1;
+}
+
+int qr_factor_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv, double* dabs, cplx* tfac, cplx* rhs, int ldr,
+                     int nrhs, const QrAsync* as) {
+  const int h = n / 2;
+  if (n % 2 != 0 || h % QP_NP != 0) { snprintf(g_errbuf, sizeof(g_errbuf), "paired qr: n=%d is not a multiple of 32", n); return -1; }
+  const bool la = as != nullptr && h > 2 * QP_NP;
+  for (int j0 = 0, k = 0; j0 < h; j0 += QP_NP, ++k) {
+    const int np = min(QP_NP, h - j0), r0 = 2 * j0, m = n - r0;
+    cplx* P = AL + (size_t)j0 * lda + r0;
+    cplx* Vp = V + (size_t)r0 * ldv + r0;
+    cplx* T = tfac + (size_t)k * QR_NB * QR_NB;
+    if (launch_panel_paired(st, P, lda, Vp, ldv, m, np, dabs + j0, h, T)) return -1;
+    const int ntrail = h - j0 - np;
+    if (!la) {
+      if (launch_larfb(st, Vp, ldv, m, T, 1, P + (size_t)np * lda, lda, ntrail, 1)) return -1;
+      if (rhs && launch_larfb(st, Vp, ldv, m, T, 1, rhs + r0, ldr, nrhs, 1)) return -1;
+      continue;
+    }
+    const int nnext = min(QP_NP, ntrail);
+    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
+    if (launch_larfb(st, Vp, ldv, m, T, 1, P + (size_t)np * lda, lda, nnext, 1)) return -1;
+    CUDA_TRY(cudaEventRecord(as->eA, st));
+    CUDA_TRY(cudaStreamWaitEvent(as->st2, as->eA, 0));
+    if (launch_larfb(as->st2, Vp, ldv, m, T, 1, P + (size_t)(np + nnext) * lda, lda, ntrail - nnext, 1)) return -1;
+    if (rhs && launch_larfb(as->st2, Vp, ldv, m, T, 1, rhs + r0, ldr, nrhs, 1)) return -1;
+    CUDA_TRY(cudaEventRecord(as->eB, as->st2));
+  }
+  if (la) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
+  return 0;
+}
+
 // =====================================================================================================
 // Triangular solve with many right-hand sides: every CTA owns 8 columns of Y in shared memory and runs the
 // whole blocked back substitution for them (inverted 32x32 diagonal blocks, DMMA updates streaming R from L2).
@@ -727,6 +1090,41 @@ __global__ void __launch_bounds__(32) trtri_diag_kernel(const cplx* __restrict__
       for (int k = i + 1; k < QR_NB; ++k)
         if (k <= j) { cplx t = cmul(R[i][k], x[k]); acc = csub(acc, t); }
       x[i] = cdiv(acc, R[i][i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < QR_NB; ++i) inv[(size_t)kb * QR_NB * QR_NB + (size_t)j * QR_NB + i] = x[i];
+}
+
+// Same for a QUATERNION upper triangle (the R of the paired factorization with rows and columns pair-interleaved): upper
+// triangular in 2x2 blocks, diagonal blocks [[e, -conj(o)], [o, conj(e)]] (inverse = conjugate transpose / (|e|^2 + |o|^2)).
+__global__ void __launch_bounds__(32) trtri_diag_quat_kernel(const cplx* __restrict__ A, int lda, int n, cplx* __restrict__ inv) {
+  __shared__ cplx R[QR_NB][QR_NB + 1];
+  const int kb = blockIdx.x, j0 = kb * QR_NB, nb = min(QR_NB, n - j0), j = threadIdx.x;
+  for (int c = 0; c < QR_NB; ++c) {
+    cplx v = cmake(0.0, 0.0);
+    if (j < nb && c < nb && (j | 1) <= (c | 1)) v = A[(size_t)(j0 + c) * lda + j0 + j];
+    if (j == c && j >= nb) v = cmake(1.0, 0.0);
+    R[j][c] = v;
+  }
+  __syncwarp();
+  cplx x[QR_NB];
+#pragma unroll
+  for (int i = 0; i < QR_NB; ++i) x[i] = cmake(0.0, 0.0);
+  // column j of the inverse: block back substitution of R x = e_j, one row pair per step (fully unrolled: x in registers)
+#pragma unroll
+  for (int p = QR_NB / 2 - 1; p >= 0; --p) {
+    const int i = 2 * p;
+    if (i <= j) {
+      cplx a0 = cmake(i == j ? 1.0 : 0.0, 0.0), a1 = cmake(i + 1 == j ? 1.0 : 0.0, 0.0);
+#pragma unroll
+      for (int k = i + 2; k < QR_NB; ++k)
+        if (k <= (j | 1)) { a0 = csub(a0, cmul(R[i][k], x[k])); a1 = csub(a1, cmul(R[i + 1][k], x[k])); }
+      // diagonal block [[r00, r01], [r10, r11]]: general 2x2 inverse (robust to the block being only approximately a quaternion)
+      const cplx r00 = R[i][i], r01 = R[i][i + 1], r10 = R[i + 1][i], r11 = R[i + 1][i + 1];
+      const cplx det = csub(cmul(r00, r11), cmul(r01, r10));
+      x[i] = cdiv(csub(cmul(r11, a0), cmul(r01, a1)), det);
+      x[i + 1] = cdiv(csub(cmul(r00, a1), cmul(r10, a0)), det);
     }
   }
 #pragma unroll
@@ -837,9 +1235,10 @@ static int trsm_block(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, i
 // diagonal blocks, the rectangular part of R goes through ZGEMM.
 #define TRSM_BS 512
 int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
-               const double* rowscale, int num_sms) {
+               const double* rowscale, int num_sms, int quat) {
   const int nblk = (n + QR_NB - 1) / QR_NB;
-  trtri_diag_kernel<<<nblk, 32, 0, st>>>(A, lda, n, work);
+  if (quat) trtri_diag_quat_kernel<<<nblk, 32, 0, st>>>(A, lda, n, work);
+  else trtri_diag_kernel<<<nblk, 32, 0, st>>>(A, lda, n, work);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   static const bool split = getenv("DQMC_TRSM_NOSPLIT") == nullptr;

@@ -22,8 +22,15 @@ int qr_factor(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs,
 // Q (n x n, explicit) from the output of qr_factor.
 int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, cplx* Q, int ldq, int num_sms);
 // X = R^{-1} Y in place in Y (n x nrhs); R = upper triangle of A.  work: ceil(n/32)*1024 cplx.
+// quat = 1: R is a QUATERNION upper triangle (2x2 diagonal blocks), as produced by qr_factor_paired + expand_R_paired.
 int trsm_upper(cudaStream_t st, const cplx* A, int lda, int n, cplx* Y, int ldy, int nrhs, cplx* work,
-               const double* rowscale, int num_sms);
+               const double* rowscale, int num_sms, int quat = 0);
+// Householder QR of a matrix with the antiunitary flavour symmetry [[A, B], [-conj(B), conj(A)]], held as its left half with
+// pair-interleaved rows (AL: n x n/2): n/2 paired steps (qr.cu, "PAIRED panel factorization").  In place: the quaternion upper
+// triangle R_L with exact zeros below; V (n x n scratch) receives the explicit reflector blocks; dabs[0:n/2] and dabs[n/2:n] =
+// moduli of the quaternion diagonal; rhs (n x nrhs, pair-interleaved rows) <- Q^H rhs.  n must be a multiple of 32.
+int qr_factor_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv, double* dabs, cplx* tfac, cplx* rhs, int ldr,
+                     int nrhs, const QrAsync* as);
 // bench hook: the panel factorizations of qr_factor without any trailing update
 int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* dabs, cplx* tfac);
 

@@ -368,6 +368,26 @@ class DQMC:
     def kernel_launches(self):
         return int(self.lib.dqmc_kernel_launches(self._ctx))
 
+    def test_qr_paired(self, XL, rhs, lookahead=True):
+        """Paired Householder QR (half-matrix path) on host data: XL, rhs n x n/2 with pair-interleaved rows.
+        Returns R_L, Q^H rhs, V (n x n explicit reflector blocks), T factors (n/32, 32, 32), dabs (n)."""
+        n, h = self.n, self.n // 2
+        x = _l.cplx_in(XL, (n, h)).copy(order="F")
+        r = _l.cplx_in(rhs, (n, h)).copy(order="F")
+        V = _l.cplx_buf((n, n))
+        Tf = np.zeros((n // 32, 32, 32), dtype=np.complex128)
+        dabs = np.zeros(n)
+        self._chk(self.lib.dqmc_test_qr_paired(self._ctx, _l.dptr(x), _l.dptr(r), _l.dptr(V), _l.dptr(Tf), _l.dptr(dabs), int(lookahead)))
+        return x, r, V, Tf.transpose(0, 2, 1).copy(), dabs      # T factors are column-major on the device
+
+    def test_udt(self, X, paired):
+        """The sweep's decompose_udt! (sort-once QR, or the paired half-matrix one for a symmetric X) -> U, D, T."""
+        n = self.n
+        x = _l.cplx_in(X, (n, n))
+        U, T, D = _l.cplx_buf((n, n)), _l.cplx_buf((n, n)), np.zeros(n)
+        self._chk(self.lib.dqmc_test_udt(self._ctx, _l.dptr(x), _l.dptr(U), _l.dptr(D), _l.dptr(T), int(paired)))
+        return U, D, T
+
     def test_zgemm(self, opA, opB, A, B, Cmat=None, alpha=1.0, beta=0.0):
         A = np.asfortranarray(A, dtype=np.complex128)
         B = np.asfortranarray(B, dtype=np.complex128)

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dqmc_bench_kernel": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "dqmc_test_zgemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, C.c_int, _D, C.c_int, _D, _D,
                                   C.c_int]),
+    "dqmc_test_qr_paired": (C.c_int, [_P, _D, _D, _D, _D, _D, C.c_int32]),
+    "dqmc_test_udt": (C.c_int, [_P, _D, _D, _D, _D, C.c_int32]),
     "dqmc_lu_profile": (C.c_int, [_P, C.c_int32, _I64]),
     "dqmc_qr_profile": (C.c_int, [_P, C.c_int32, _I64]),
     "dqmc_kernel_launches": (C.c_int64, [_P]),

@@ -159,6 +159,11 @@ int dqmc_bench_kernel(dqmc_ctx* ctx, int which, int reps, double* ms_per_launch)
 /* C = alpha*op(A)*op(B) + beta*C on host matrices through the hand-written kernel (test hook); op: 0 N, 1 T, 2 C */
 int dqmc_test_zgemm(dqmc_ctx* ctx, int opA, int opB, int M, int N, int K, const double* alpha, const double* A, int lda,
                     const double* B, int ldb, const double* beta, double* C, int ldc);
+/* test hooks of the half-matrix (antiunitary-symmetric) stabilization path: the paired Householder QR on host data (XL, rhs:
+ * n x n/2 complex, pair-interleaved rows; V: n x n; Tfac: n/32 blocks of 32 x 32; dabs: n), and the sweep's decompose_udt! on a
+ * host matrix (linalg.jl:20-39) through the sort-once QR (paired = 0) or the paired one (paired = 1, symmetric input) */
+int dqmc_test_qr_paired(dqmc_ctx* ctx, double* XL, double* rhs, double* V, double* Tfac, double* dabs, int32_t lookahead);
+int dqmc_test_udt(dqmc_ctx* ctx, const double* x, double* U, double* D, double* T, int32_t paired);
 /* cycle counters of the last local_updates launch: [0] total, [1] stage 1, [2] stage 2, [3] flush, [4] #flushes,
  * [5] accepts, [8..15] per-warp stage-1 time, [16..23] per-warp role time before the speculative part,
  * [24..26] flush: first grid barrier, tiles, second grid barrier (debug; 32 values) */
