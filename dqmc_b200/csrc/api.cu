@@ -555,9 +555,9 @@ static void push_B(dqmc_ctx* c, Chain& ch, int op, int slice) {
 }
 static bool op_is_rows(int op) { return op == DQMC_B_RIGHT || op == DQMC_B_INV_RIGHT; }
 
-static int run_chain(dqmc_ctx* c, bool rows, cplx* mat, const Chain& ch, const double* colscale, double* colnorm2) {
+static int run_chain(dqmc_ctx* c, bool rows, cplx* mat, const Chain& ch, const double* colscale, double* colnorm2, int nvtot = 0) {
   return launch_apply_chain(rows, mat, c->n, c->n, ch, c->hs, c->N, c->p.lambda * c->p.delta_tau, colscale, colnorm2,
-                            c->num_sms, c->st);
+                            c->num_sms, c->st, nvtot);
 }
 
 static int apply_B(dqmc_ctx* c, int op, int slice, cplx* mat) {
@@ -640,7 +640,10 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
   const int n = c->n;
   const size_t nn = (size_t)n * n;
   const int src = left ? idx : idx + 1, dst = left ? idx + 1 : idx;
-  CU(c, cudaMemcpyAsync(c->W[0], uslab(c, src), sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st));
+  // half-matrix path: B ... B U D is symmetric and the paired UDT reads its left-half columns only
+  const bool paired = !c->udt_qrcp_sweep && use_paired(c);
+  const int ncols = paired ? n / 2 : n;
+  CU(c, cudaMemcpyAsync(c->W[0], uslab(c, src), sizeof(cplx) * (paired ? nn / 2 : nn), cudaMemcpyDeviceToDevice, c->st));
   const int lo = 1 + (idx - 1) * c->sm, hi = idx * c->sm;       // s.ranges[idx]
   Chain ch; ch.nsteps = 0;
   for (int k = 0; k < c->sm; ++k) {
@@ -648,7 +651,7 @@ static int add_slice_sequence(dqmc_ctx* c, int idx, bool left) {
     const bool last = (k == c->sm - 1);
     push_B(c, ch, left ? DQMC_B_LEFT : DQMC_B_DAGGER_LEFT, slice);
     if (last || ch.nsteps + 4 > DQMC_MAX_CHAIN) {
-      TRY(c, run_chain(c, false, c->W[0], ch, last ? dslab(c, src) : nullptr, last ? c->colnorm : nullptr));
+      TRY(c, run_chain(c, false, c->W[0], ch, last ? dslab(c, src) : nullptr, last ? c->colnorm : nullptr, ncols));
       ch.nsteps = 0;
     }
   }

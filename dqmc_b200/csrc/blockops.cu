@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
                                                           Chain chain, const double* __restrict__ hsfield,
                                                           int nsites, double lam_dtau,
                                                           const double* __restrict__ colscale,
-                                                          double* __restrict__ colnorm2) {
+                                                          double* __restrict__ colnorm2, int nvtot) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ldx = ROWS ? n + 1 : n;
   cplx* x = reinterpret_cast<cplx*>(smem_raw);
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
   __shared__ double red[8];
 
   const int v0 = blockIdx.x * nvec_cta;
-  const int nvec = min(nvec_cta, n - v0);
+  const int nvec = min(nvec_cta, nvtot - v0);   // nvtot vectors in all (n, or the n/2 left-half columns of a symmetric matrix)
   const int tid = threadIdx.x;
 
   // ---- global -> shared.  COLS: one TMA bulk copy per column; ROWS: 16-byte cp.async copies, all in flight at once
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
 
 int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, const double* hsfield,
                        int nsites, double lam_dtau, const double* colscale, double* colnorm2,
-                       int num_sms, cudaStream_t stream) {
+                       int num_sms, cudaStream_t stream, int nvtot) {
+  if (nvtot <= 0 || nvtot > n) nvtot = n;
   const size_t smem_cap = 200 * 1024;
   const size_t tab_bytes = sizeof(double4) * (size_t)nsites;
   const int ldx = rows ? n + 1 : n;
@@ -225,21 +226,21 @@ int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, 
   int nvec;
   if (rows) {
     nvec = 8;                                   // 128 B contiguous per column
-    while (nvec > 1 && ((n + nvec - 1) / nvec < num_sms / 2 || nvec > nvec_max)) nvec >>= 1;
+    while (nvec > 1 && ((nvtot + nvec - 1) / nvec < num_sms / 2 || nvec > nvec_max)) nvec >>= 1;
   } else {
-    nvec = (n + num_sms - 1) / num_sms;
+    nvec = (nvtot + num_sms - 1) / num_sms;
     if (nvec > nvec_max) nvec = nvec_max;
     if (nvec < 1) nvec = 1;
   }
-  const int grid = (n + nvec - 1) / nvec;
+  const int grid = (nvtot + nvec - 1) / nvec;
   const size_t smem = sizeof(cplx) * (size_t)nvec * ldx + tab_bytes;
   static SmemMemo memo_cols, memo_rows;
   if (ensure_max_dynamic_smem(apply_chain_kernel<false>, memo_cols, nullptr)) return -1;
   if (ensure_max_dynamic_smem(apply_chain_kernel<true>, memo_rows, nullptr)) return -1;
   if (rows)
-    apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2);
+    apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot);
   else
-    apply_chain_kernel<false><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2);
+    apply_chain_kernel<false><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;

@@ -33,4 +33,4 @@ struct Chain {
 
 int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, const double* hsfield,
                        int nsites, double lam_dtau, const double* colscale, double* colnorm2,
-                       int num_sms, cudaStream_t stream);
+                       int num_sms, cudaStream_t stream, int nvtot = 0);   // nvtot: vectors to process (0 = all n)
