@@ -1550,6 +1550,15 @@ extern "C" int dqmc_bench_kernel(dqmc_ctx* c, int which, int reps, double* ms_pe
         rc = cudaMemcpyAsync(c->W[1], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
         if (!rc) rc = qr_factor(c->st, c->W[1], n, n, c->tau, c->dabs, c->tfac, c->W[3], n, n, c->num_sms, c->lookahead ? &c->qra : nullptr);
         break;
+      case 15:   // paired QR of a left half with Q^H applied to n/2 right-hand sides (the shape of both paired call sites)
+      case 17:   // ... without right-hand sides
+        rc = cudaMemcpyAsync(c->W[1], c->W[4], sizeof(cplx) * nn, cudaMemcpyDeviceToDevice, c->st) != cudaSuccess;
+        if (!rc) rc = qr_factor_paired(c->st, c->W[1], n, n, c->W[3], n, c->dabs, c->tfac, which == 15 ? c->W[1] + nn / 2 : nullptr, n, n / 2,
+                                       c->lookahead ? &c->qra : nullptr);
+        break;
+      case 16:   // the serial paired panel chain alone
+        rc = qr_panels_only_paired(c->st, c->W[1], n, n, c->W[3], n, c->dabs, c->tfac);
+        break;
       default: rc = -1; snprintf(g_errbuf, sizeof(g_errbuf), "dqmc_bench_kernel: unknown kernel %d", which);
     }
   }

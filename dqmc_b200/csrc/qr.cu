@@ -617,13 +617,17 @@ __device__ __forceinline__ cplx vmask_load(const cplx* __restrict__ V, int ldv, 
 
 __global__ void __launch_bounds__(256)
 larfb_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict__ T, int conjT,
-             cplx* __restrict__ C, int ldc, int ncols, int vmode) {
+             cplx* __restrict__ C, int ldc, int ncols, int vmode, cplx* __restrict__ Cb, int ldcb, int ncolsb) {
   __shared__ cplx Tsm[QR_NB][QR_NB + 1];
   __shared__ double Wp[4][4][32][4];
   __shared__ cplx W1[QR_NB][8], W2[QR_NB][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lo = lane >> 2, lk = lane & 3;
-  const int c0 = blockIdx.x * 8;
+  // two target matrices in one launch (the trailing columns and the right-hand side of a factorization: together they fill
+  // the GPU, one after the other they take two latency-bound waves): column blocks [0, nblk_a) belong to C, the rest to Cb
+  const int nblk_a = (ncols + 7) / 8;
+  int c0 = blockIdx.x * 8;
+  if ((int)blockIdx.x >= nblk_a) { C = Cb; ldc = ldcb; ncols = ncolsb; c0 = ((int)blockIdx.x - nblk_a) * 8; }
 
   for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) Tsm[e % QR_NB][e / QR_NB] = T[e];
 
@@ -937,7 +941,21 @@ static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cp
     g_launches++;
     return 0;
   }
-  larfb_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, C, ldc, ncols, vmode);
+  larfb_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, C, ldc, ncols, vmode, nullptr, 0, 0);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+// the same block reflector applied to two matrices (either may be empty) in one launch of the wide kernel
+static int launch_larfb2(cudaStream_t st, const cplx* V, int ldv, int m, const cplx* T, int conjT, cplx* Ca, int ldca, int ncolsa,
+                         cplx* Cb, int ldcb, int ncolsb, int vmode) {
+  if (ncolsa <= 0) return launch_larfb(st, V, ldv, m, T, conjT, Cb, ldcb, ncolsb, vmode);
+  if (ncolsb <= 0) return launch_larfb(st, V, ldv, m, T, conjT, Ca, ldca, ncolsa, vmode);
+  if (ncolsa + ncolsb <= g_larfb_cluster_max_cols && m >= 64) {   // few columns: two launches of the row-split cluster kernel
+    if (launch_larfb(st, V, ldv, m, T, conjT, Ca, ldca, ncolsa, vmode)) return -1;
+    return launch_larfb(st, V, ldv, m, T, conjT, Cb, ldcb, ncolsb, vmode);
+  }
+  larfb_kernel<<<(ncolsa + 7) / 8 + (ncolsb + 7) / 8, 256, 0, st>>>(V, ldv, m, T, conjT, Ca, ldca, ncolsa, vmode, Cb, ldcb, ncolsb);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
@@ -1056,11 +1074,21 @@ int qr_factor_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv
     if (launch_larfb(st, Vp, ldv, m, T, 1, P + (size_t)np * lda, lda, nnext, 1)) return -1;
     CUDA_TRY(cudaEventRecord(as->eA, st));
     CUDA_TRY(cudaStreamWaitEvent(as->st2, as->eA, 0));
-    if (launch_larfb(as->st2, Vp, ldv, m, T, 1, P + (size_t)(np + nnext) * lda, lda, ntrail - nnext, 1)) return -1;
-    if (rhs && launch_larfb(as->st2, Vp, ldv, m, T, 1, rhs + r0, ldr, nrhs, 1)) return -1;
+    if (launch_larfb2(as->st2, Vp, ldv, m, T, 1, P + (size_t)(np + nnext) * lda, lda, ntrail - nnext, rhs ? rhs + r0 : nullptr, ldr,
+                      rhs ? nrhs : 0, 1))
+      return -1;
     CUDA_TRY(cudaEventRecord(as->eB, as->st2));
   }
   if (la) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
+  return 0;
+}
+
+int qr_panels_only_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv, double* dabs, cplx* tfac) {
+  const int h = n / 2;
+  for (int j0 = 0, k = 0; j0 < h; j0 += QP_NP, ++k)
+    if (launch_panel_paired(st, AL + (size_t)j0 * lda + 2 * j0, lda, V + (size_t)(2 * j0) * ldv + 2 * j0, ldv, n - 2 * j0, min(QP_NP, h - j0),
+                            dabs + j0, h, tfac + (size_t)k * QR_NB * QR_NB))
+      return -1;
   return 0;
 }
 

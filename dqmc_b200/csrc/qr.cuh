@@ -39,3 +39,5 @@ int qr_panels_only(cudaStream_t st, cplx* A, int lda, int n, cplx* tau, double* 
 // vn, rdiag: n doubles of scratch each; bar: one unsigned int of scratch.
 int qrcp_udt(cudaStream_t st, cplx* A, int lda, int n, cplx* QH, int ldq, cplx* T, int ldt, double* dabs, double* vn, double* rdiag,
              int* perm, int* pos, unsigned int* bar, int num_sms);
+// bench hook: the paired panel factorizations alone
+int qr_panels_only_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv, double* dabs, cplx* tfac);

@@ -1,0 +1,6 @@
+#!/bin/bash
+TAG=${1:-r03c}
+OUT=gpurun_out; mkdir -p $OUT
+timeout 200 python tools/stab_breakdown.py 16 > $OUT/${TAG}_stab.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_paired.py tests/test_gpu_headline.py -x -q -m gpu -k "paired or propagation" > $OUT/${TAG}_pytest.log 2>&1
+cat $OUT/${TAG}_stab.log; tail -3 $OUT/${TAG}_pytest.log
