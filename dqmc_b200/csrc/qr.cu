@@ -334,16 +334,38 @@ struct PairedSmem {
   cplx rowl[QR_NB];                   // row pair j of the panel (rank 0): slot c = e, slot c+16 = o
   cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][slot]
   cplx rowv[2][QR_NB];                // [parity][slot]: row pair j (pushed by rank 0)
-  cplx Tsm[QR_NB][QR_NB + 1];         // compact-WY T; rows {g, g+8, g+16, g+24} belong to warp g
-  cplx gsm[8][2][QR_NB];              // per warp: V^H v_j and V^H psi(v_j)
+  cplx Tsm[QR_NB][QR_NB + 1];         // compact-WY T; rows {2g, 2g+1, 2g+16, 2g+17} belong to warp g
+  cplx gsm[2][2][QR_NB];              // [parity of the step][0]: V^H v_j, written by warp 0, read by all in the next step
+  cplx ab[2][QR_NB];                  // update coefficients alpha / beta of the step per lane (warp 0 -> all warps)
+  cplx sc4[4];                        // u_j and x_j on row pair j (e, o)
   cplx udiag[QR_NB];                  // v_j on its own row pair: slot j = e, slot j+16 = o
-  double tau_s[QP_NP], nx_s[QP_NP];
+  double tau_s[QP_NP], nx_s[QP_NP], rn_s[QP_NP];
   unsigned long long full[2];
 };
 
-// one column of T (zlarft, forward / columnwise) by warp g for its rows i = g + 8q: T(i, col) = -tau sum_{k=i}^{col-1} T(i,k) gv(k)
-__device__ __forceinline__ void paired_t_column(PairedSmem& S, int g, int lane, int col, double tau, const cplx* gv) {
-  const int q = lane >> 3, hh = lane & 7, i = g + 8 * q;
+// 1/sqrt(a) and 1/a for normal a > 0: hardware approximation (2^-22 / 2^-23) + two Newton steps
+__device__ __forceinline__ double rsqrt_nr(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-(a * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-(a * y), y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ double rcp_nr(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+
+// The two columns 2j, 2j+1 of T (zlarft, forward / columnwise) of pair-step j.  Warp g owns the rows {2g, 2g+1, 2g+16, 2g+17} (whole
+// quaternion rows): column 2j is T(i, 2j) = -tau sum_{k=i}^{2j-1} T(i,k) gv(k); column 2j+1 follows from the quaternion structure
+// of T (exact: paired_panel_spec.py), T(2c, 2j+1) = -conj(T(2c+1, 2j)), T(2c+1, 2j+1) = conj(T(2c, 2j)), T(2j, 2j+1) = 0.
+__device__ __forceinline__ void paired_t_columns(PairedSmem& S, int g, int lane, int j, double tau, const cplx* gv) {
+  const int q = lane >> 3, hh = lane & 7, i = 2 * g + (q & 1) + 16 * (q >> 1), col = 2 * j;
   cplx acc = cmake(0.0, 0.0);
   if (i < col) {
 #pragma unroll
@@ -357,18 +379,34 @@ __device__ __forceinline__ void paired_t_column(PairedSmem& S, int g, int lane, 
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
   }
+  // lanes of row i and of its partner row i^1 are 8 apart (q ^ 1): fetch the partner's sum
+  const cplx oth = cmake(__shfl_xor_sync(0xffffffffu, acc.x, 8), __shfl_xor_sync(0xffffffffu, acc.y, 8));
   if (hh == 0) {
-    if (i < col) S.Tsm[i][col] = cmake(-tau * acc.x, -tau * acc.y);
-    else if (i == col) S.Tsm[i][i] = cmake(tau, 0.0);
+    if (i < col) {
+      S.Tsm[i][col] = cmake(-tau * acc.x, -tau * acc.y);
+      // T(i, col+1) from T(i^1, col) = -tau oth:  i even: -conj(.),  i odd: conj(.)
+      S.Tsm[i][col + 1] = (i & 1) ? cmake(-tau * oth.x, tau * oth.y) : cmake(tau * oth.x, -tau * oth.y);
+    } else if (i == col) {
+      S.Tsm[i][i] = cmake(tau, 0.0);
+      S.Tsm[i][i + 1] = cmake(0.0, 0.0);
+    } else if (i == col + 1) {
+      S.Tsm[i][i] = cmake(tau, 0.0);
+    }
   }
   __syncwarp();
 }
 
-template <int T, bool GENERAL>
+template <int T, bool GENERAL, bool PROF>
 __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
                                                   cplx* __restrict__ Vout, int ldv, int m, int np, int r_begin, int nloc,
-                                                  double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout) {
+                                                  double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout,
+                                                  long long* __restrict__ prof, int prof_rank) {
   constexpr int NW = 8;
+  // PROF instantiation only: cycle stamps of thread 0 of cluster rank `prof_rank`: [0] dots [1] reduce + push [2] T columns
+  // [3] wait for the exchange [4] parameters [5] update [6] epilogue (stores) [7] pair-steps
+  long long pcyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = PROF ? clock64() : 0;
+  const bool stamp = PROF && prof != nullptr && (int)cl.block_rank() == prof_rank && threadIdx.x == 0;
+#define QSTAMP(k) do { if (PROF && stamp) { const long long t_ = clock64(); pcyc[k] += t_ - tprev; tprev = t_; } } while (0)
   constexpr bool KEEP = (T <= 10);               // current column kept in registers between the dot and the update phase
   const int rank = (int)cl.block_rank();
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
@@ -393,6 +431,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
 
   double tau_prev = 0.0;
   double sc = 1.0;                               // 1/|x| of my column once it is finished (v = sc * u)
+  if (PROF) tprev = clock64();
   for (int j = 0; j < np; ++j) {
     const int par = j & 1;
     if (tid == 0)
@@ -420,6 +459,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
           if (g + NW * t == j) S.rowl[lane] = (col < j) ? cscale(x[t], sc) : x[t];
       }
     }
+    QSTAMP(0);
     __syncthreads();
     {
       // warp g sums the 8 partials of slot `lane` and pushes the result (and row pair j, if mine) to CTA g of the cluster
@@ -430,68 +470,77 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
       st_async_c16(r_xch + par * (QR_CL * QR_NB * 16), tot, r_bar + 8 * par);
       if (GENERAL) st_async_c16(r_row + par * (QR_NB * 16), S.rowl[lane], r_bar + 8 * par);
     }
+    QSTAMP(1);
     if (doT && j > 0) {
       // the two T columns of the previous pair-step, in the shadow of the exchange
-      paired_t_column(S, g, lane, 2 * (j - 1), tau_prev, S.gsm[g][0]);
-      paired_t_column(S, g, lane, 2 * (j - 1) + 1, tau_prev, S.gsm[g][1]);
+      paired_t_columns(S, g, lane, j - 1, tau_prev, S.gsm[par ^ 1][0]);
     }
+    QSTAMP(2);
     mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
-    // ---- phase C: totals and reflector parameters (every thread, redundantly, from local shared memory)
-    cplx tc;
-    double tj;
-    {
-      const cplx c0 = cadd(S.xch[par][0][lane], S.xch[par][1][lane]), c1 = cadd(S.xch[par][2][lane], S.xch[par][3][lane]);
-      const cplx c2 = cadd(S.xch[par][4][lane], S.xch[par][5][lane]), c3 = cadd(S.xch[par][6][lane], S.xch[par][7][lane]);
-      const double j0 = S.xch[par][0][j].x + S.xch[par][1][j].x, j1 = S.xch[par][2][j].x + S.xch[par][3][j].x;
-      const double j2 = S.xch[par][4][j].x + S.xch[par][5][j].x, j3 = S.xch[par][6][j].x + S.xch[par][7][j].x;
-      tc = cadd(cadd(c0, c1), cadd(c2, c3));
-      tj = (j0 + j1) + (j2 + j3);
-    }
-    const cplx tother = cmake(__shfl_xor_sync(0xffffffffu, tc.x, 16), __shfl_xor_sync(0xffffffffu, tc.y, 16));
-    const cplx D1 = comp == 0 ? tc : tother, D2 = comp == 0 ? tother : tc;
-    const cplx xe0 = S.rowv[par][j], xo0 = S.rowv[par][j + 16];
-    const cplx ce0 = S.rowv[par][col], co0 = S.rowv[par][col + 16];
-    const double q2 = cabs2(xe0) + cabs2(xo0);
-    const double nrm2 = q2 + tj;
-    double f = 0.0, rnj = 0.0, tau = 0.0, nx = 0.0;
-    cplx ue0 = cmake(0.0, 0.0), uo0 = ue0;
-    if (nrm2 > 0.0) {
-      nx = sqrt(nrm2);
-      const double q = sqrt(q2);
-      f = 1.0 / (nx * (nx + q));
-      if (q > 0.0) {
-        const double s1 = (q + nx) / q;
-        ue0 = cscale(xe0, s1); uo0 = cscale(xo0, s1);
-      } else {
-        ue0 = cmake(nx, 0.0);
+    QSTAMP(3);
+    // ---- phase C: totals and reflector parameters.  Identical for every warp of the CTA, and the FP64 pipe is the bottleneck
+    // when all eight evaluate the square roots and divisions at once (1160 cycles per step measured): warp 0 alone computes
+    // them and broadcasts the per-column update coefficients through shared memory (~500 cycles).
+    if (g == 0) {
+      cplx tc;
+      {
+        const cplx c0 = cadd(S.xch[par][0][lane], S.xch[par][1][lane]), c1 = cadd(S.xch[par][2][lane], S.xch[par][3][lane]);
+        const cplx c2 = cadd(S.xch[par][4][lane], S.xch[par][5][lane]), c3 = cadd(S.xch[par][6][lane], S.xch[par][7][lane]);
+        tc = cadd(cadd(c0, c1), cadd(c2, c3));
       }
-      rnj = (nx + q) * f;                        // 1 / |x|
-      tau = nx * nx * f;                         // |x| / (|x| + |x_j|)
+      const double tj = __shfl_sync(0xffffffffu, tc.x, j);        // D1 of the current column = |x|^2 below row pair j
+      const cplx tother = cmake(__shfl_xor_sync(0xffffffffu, tc.x, 16), __shfl_xor_sync(0xffffffffu, tc.y, 16));
+      const cplx D1 = comp == 0 ? tc : tother, D2 = comp == 0 ? tother : tc;
+      const cplx xe0 = S.rowv[par][j], xo0 = S.rowv[par][j + 16];
+      const cplx ce0 = S.rowv[par][col], co0 = S.rowv[par][col + 16];
+      const double q2 = cabs2(xe0) + cabs2(xo0);
+      const double nrm2 = q2 + tj;
+      // The square roots and divisions of the reflector are the longest dependent chain of a step (sqrt, sqrt, 1/x, x/y one after
+      // the other: ~1000 cycles measured).  Reciprocal square roots from the hardware approximation + two Newton steps (1-2 ulp,
+      // no slow-path branches, the two chains interleave): |x| = nrm2 r, 1/|x| = r, |x_j| = q2 rq, |x|/|x_j| = |x| rq, and ONE
+      // reciprocal 1 / (|x| + |x_j|).  A relative error eps in |x| leaves H unitary up to O(eps), like any rounding of tau.
+      const bool nzx = nrm2 > 0.0, nzq = q2 > 0.0;
+      const double r = nzx ? rsqrt_nr(nrm2) : 0.0, rq = nzq ? rsqrt_nr(q2) : 0.0;
+      const double nx = nrm2 * r, q = q2 * rq;
+      const double gi = nzx ? rcp_nr(nx + q) : 0.0;
+      const double f = r * gi;                     // 1 / (|x| (|x| + |x_j|))
+      const double rnj = r;                        // 1 / |x|
+      const double tau = nx * gi;                  // |x| / (|x| + |x_j|)
+      // products with row pair j that do not depend on the scale: t1 = x_j^H c_j, t2 = psi(x_j)^H c_j (in parallel with the chain above)
+      cplx t1 = cmake(0.0, 0.0), t2 = t1;
+      cfma_conj(t1, xe0, ce0); cfma_conj(t1, xo0, co0);
+      cfma(t2, xe0, co0); cfma(t2, cneg(xo0), ce0);
+      // u_j = s1 x_j, s1 = 1 + |x| / |x_j|;  x_j = 0: u_j = (|x|, 0), i.e. u^H c = D1 + |x| c_e, psi(u)^H c = D2 + |x| c_o
+      const double s1 = nzq ? fma(nx, rq, 1.0) : nx;
+      if (!nzq) { t1 = ce0; t2 = co0; }
+      const cplx ue0 = nzq ? cscale(xe0, s1) : cmake(nx, 0.0), uo0 = nzq ? cscale(xo0, s1) : cmake(0.0, 0.0);
+      // uc = u^H c = D1 + s1 t1,   pc = psi(u)^H c = D2 + s1 t2
+      const cplx uc = cmake(fma(s1, t1.x, D1.x), fma(s1, t1.y, D1.y)), pc = cmake(fma(s1, t2.x, D2.x), fma(s1, t2.y, D2.y));
+      if (doT && comp == 0) {
+        // Gram entries against the finished columns (their dots and row entries arrived scaled by 1/|x_c|)
+        const bool fin = col < j;
+        const cplx z = cmake(0.0, 0.0);
+        S.gsm[par][0][2 * col] = fin ? cmake(rnj * uc.x, -rnj * uc.y) : z;        // v_c^H v_j        =  conj(uc)
+        S.gsm[par][0][2 * col + 1] = fin ? cmake(-rnj * pc.x, -rnj * pc.y) : z;   // psi(v_c)^H v_j   = -pc
+        // (the entries against psi(v_j), conj(pc) and uc, are not needed: column 2j+1 of T follows from column 2j)
+      }
+      // update coefficients of my column: alpha = -f uc, beta = +-f pc (e / o lanes), zero for the finished columns
+      const bool upd = col > j;
+      const double fb = comp == 0 ? f : -f;
+      S.ab[0][lane] = upd ? cmake(-f * uc.x, -f * uc.y) : cmake(0.0, 0.0);
+      S.ab[1][lane] = upd ? cmake(fb * pc.x, fb * pc.y) : cmake(0.0, 0.0);
+      if (lane == 0) {
+        S.tau_s[j] = tau; S.nx_s[j] = nx; S.rn_s[j] = rnj;
+        S.udiag[j] = cscale(ue0, rnj); S.udiag[j + 16] = cscale(uo0, rnj);
+        S.sc4[0] = ue0; S.sc4[1] = uo0; S.sc4[2] = xe0; S.sc4[3] = xo0;
+      }
     }
-    // uc = u^H c = D1 + conj(ue0) ce0 + conj(uo0) co0,   pc = psi(u)^H c = D2 + ue0 co0 - uo0 ce0
-    cplx uc = D1, pc = D2;
-    cfma_conj(uc, ue0, ce0); cfma_conj(uc, uo0, co0);
-    cfma(pc, ue0, co0); cfma(pc, cneg(uo0), ce0);
-    if (doT && comp == 0) {
-      // Gram entries against the finished columns (their dots and row entries arrived scaled by 1/|x_c|)
-      const bool fin = col < j;
-      const cplx z = cmake(0.0, 0.0);
-      S.gsm[g][0][2 * col] = fin ? cmake(rnj * uc.x, -rnj * uc.y) : z;        // v_c^H v_j        =  conj(uc)
-      S.gsm[g][0][2 * col + 1] = fin ? cmake(-rnj * pc.x, -rnj * pc.y) : z;   // psi(v_c)^H v_j   = -pc
-      S.gsm[g][1][2 * col] = fin ? cmake(rnj * pc.x, -rnj * pc.y) : z;        // v_c^H psi(v_j)   =  conj(pc)
-      S.gsm[g][1][2 * col + 1] = fin ? cmake(rnj * uc.x, rnj * uc.y) : z;     // psi(v_c)^H psi(v_j) = uc
-    }
-    if (tid == 0) {
-      S.tau_s[j] = tau; S.nx_s[j] = nx;
-      S.udiag[j] = cscale(ue0, rnj); S.udiag[j + 16] = cscale(uo0, rnj);
-    }
-    tau_prev = tau;
+    __syncthreads();
+    const cplx alpha = S.ab[0][lane], beta = S.ab[1][lane];
+    tau_prev = S.tau_s[j];
+    QSTAMP(4);
     // ---- phase D: c += A alpha + conj(B) beta on the rows below row pair j (A = my component of the current column,
     // B = the other one), alpha = -f uc, beta = +-f pc (e / o lanes); row pair j itself with u_j (rank 0)
-    const bool upd = col > j;
-    const cplx alpha = upd ? cmake(-f * uc.x, -f * uc.y) : cmake(0.0, 0.0);
-    const double fb = comp == 0 ? f : -f;
-    const cplx beta = upd ? cmake(fb * pc.x, fb * pc.y) : cmake(0.0, 0.0);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       cplx ca, cb;
@@ -501,23 +550,24 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
       cfma_conj(x[t], cb, beta);
       if (GENERAL) {
         if (g + NW * t == j && col >= j) {
+          const cplx ue0 = S.sc4[0], uo0 = S.sc4[1];
           const cplx myU = comp == 0 ? ue0 : uo0, otU = comp == 0 ? uo0 : ue0;
-          if (col == j) x[t] = comp == 0 ? csub(xe0, ue0) : csub(xo0, uo0);
+          if (col == j) x[t] = comp == 0 ? csub(S.sc4[2], ue0) : csub(S.sc4[3], uo0);
           else { cfma(x[t], myU, alpha); cfma_conj(x[t], otU, beta); }
         }
       }
     }
-    if (col == j) sc = rnj;
+    if (col == j) sc = S.rn_s[j];
     if (!KEEP) __syncwarp();                     // everybody has re-read the column buffer before it is overwritten
     if (col == j + 1) {
 #pragma unroll
       for (int t = 0; t < T; ++t) S.colbuf[g][comp][t] = (!GENERAL || g + NW * t > j + 1) ? x[t] : cmake(0.0, 0.0);
     }
     __syncwarp();
+    QSTAMP(5);
   }
   if (doT) {
-    paired_t_column(S, g, lane, 2 * (np - 1), tau_prev, S.gsm[g][0]);
-    paired_t_column(S, g, lane, 2 * (np - 1) + 1, tau_prev, S.gsm[g][1]);
+    paired_t_columns(S, g, lane, np - 1, tau_prev, S.gsm[(np - 1) & 1][0]);
   }
   __syncthreads();   // udiag / T complete; the staging area is free (nobody reads `a` after the initial load)
   // ---- R: rows at or above the quaternion diagonal keep their values, eliminated entries are exact zeros
@@ -562,16 +612,19 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
     if (tid < np) { dabs_out[tid] = S.nx_s[tid]; if (dabs_dup) dabs_out[dabs_dup + tid] = S.nx_s[tid]; }
   }
   cl.sync();  // no CTA may exit while others may still write into its shared memory
+  QSTAMP(6);
+  if (PROF && stamp) { for (int q = 0; q < 7; ++q) prof[q] += pcyc[q]; prof[7] += np; }
+#undef QSTAMP
 }
 
 // Row split of the paired panel: rank 0 owns the first 32 interleaved rows (16 quaternion rows, the diagonal block), the rest
 // is dealt to ranks 1..7 in whole quaternion rows.
 __host__ __device__ __forceinline__ int paired_rows_below(int m) { return 2 * ((max(0, m - QR_NB) / 2 + QR_CL - 2) / (QR_CL - 1)); }
 
-template <int T>
+template <int T, bool PROF>
 __global__ void __cluster_dims__(QR_CL, 1, 1) __launch_bounds__(256)
 qr_panel_paired_kernel(cplx* __restrict__ A, int lda, cplx* __restrict__ Vout, int ldv, int m, int np,
-                       double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout) {
+                       double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout, long long* __restrict__ prof, int prof_rank) {
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
   const int rs1 = paired_rows_below(m);
@@ -596,8 +649,8 @@ qr_panel_paired_kernel(cplx* __restrict__ A, int lda, cplx* __restrict__ Vout, i
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (rank == 0) panel_body_paired<2, true>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout);
-  else panel_body_paired<T, false>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout);
+  if (rank == 0) panel_body_paired<2, true, PROF>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
+  else panel_body_paired<T, false, PROF>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
 }
 
 // =====================================================================================================
@@ -889,6 +942,140 @@ larfb_cluster_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __r
   cl.sync();   // nobody exits while its shared memory may still be written... (all remote stores precede the first sync)
 }
 
+// The same for the 16 columns of the NEXT panel of the paired factorization -- the one block-reflector application that sits on
+// the critical path of the panel chain (once per panel).  larfb_cluster_kernel spends its 11 us on L2 round trips in sequence
+// (V fragments, then C, per 8-row step and per phase); here every global load of a CTA (<= 128 rows: two 8-row steps per warp
+// in each phase) is issued before the first use, the T product runs on four independent accumulators, and the trailing cluster
+// barrier is dropped (all remote stores precede the first one).  m <= 1024, vmode 1 (explicit V).
+__global__ void __cluster_dims__(LC_CL, 1, 1) __launch_bounds__(256)
+larfb_narrow_kernel(const cplx* __restrict__ V, int ldv, int m, const cplx* __restrict__ T, int conjT,
+                    cplx* __restrict__ C, int ldc, int ncols) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* slots = reinterpret_cast<cplx*>(smem_raw);           // [LC_CL][256]: partial W of every CTA of the cluster
+  __shared__ cplx Tsm[QR_NB][QR_NB + 1];
+  __shared__ double Wp[4][4][32][4];
+  __shared__ cplx W1[QR_NB][8], W2[QR_NB][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lo = lane >> 2, lk = lane & 3;
+  const int rank = (int)cl.block_rank();
+  const int c0 = (blockIdx.x / LC_CL) * 8;
+  const int rchunk = (((m + LC_CL - 1) / LC_CL) + 7) / 8 * 8;          // <= 128
+  const int rbeg = min(m, rank * rchunk), rend = min(m, rbeg + rchunk);
+  const cplx zero = cmake(0.0, 0.0);
+
+  // ---- every global load of this CTA, up front: phase-1 fragments (conj(V)^T, C), phase-3 fragments (V, C tile)
+  cplx a1[2][2][4], b1[2][2], a3[2][8], cv[2][2];
+  const bool colok1 = (c0 + lo) < ncols;
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int r0 = rbeg + 8 * warp + 64 * s2;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + 4 * u + lk;
+      const bool ok = r < rend;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) a1[s2][u][it] = ok ? V[(size_t)(it * 8 + lo) * ldv + r] : zero;
+      b1[s2][u] = (ok && colok1) ? C[(size_t)(c0 + lo) * ldc + r] : zero;
+    }
+    const int r3 = r0 + lo;
+    const bool ok3 = r3 < rend;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) a3[s2][kk] = ok3 ? V[(size_t)(kk * 4 + lk) * ldv + r3] : zero;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cv[s2][e] = (ok3 && c0 + 2 * lk + e < ncols) ? C[(size_t)(c0 + 2 * lk + e) * ldc + r3] : zero;
+  }
+  for (int e = tid; e < QR_NB * QR_NB; e += blockDim.x) Tsm[e % QR_NB][e / QR_NB] = T[e];
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "I am running" (waited for before the first remote store)
+
+  // ---- phase 1: partial W = V^H C over my rows (32 x 8)
+  double cr[4][2], ci[4][2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) cr[it][0] = cr[it][1] = ci[it][0] = ci[it][1] = 0.0;
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {   // A operand = conj(V)
+        dmma884(cr[it][0], cr[it][1], a1[s2][u][it].x, b1[s2][u].x);
+        dmma884(cr[it][0], cr[it][1], a1[s2][u][it].y, b1[s2][u].y);
+        dmma884(ci[it][0], ci[it][1], a1[s2][u][it].x, b1[s2][u].y);
+        dmma884(ci[it][0], ci[it][1], -a1[s2][u][it].y, b1[s2][u].x);
+      }
+  if (warp >= 4) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      Wp[warp - 4][it][lane][0] = cr[it][0]; Wp[warp - 4][it][lane][1] = cr[it][1];
+      Wp[warp - 4][it][lane][2] = ci[it][0]; Wp[warp - 4][it][lane][3] = ci[it][1];
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      Wp[warp][it][lane][0] += cr[it][0]; Wp[warp][it][lane][1] += cr[it][1];
+      Wp[warp][it][lane][2] += ci[it][0]; Wp[warp][it][lane][3] += ci[it][1];
+    }
+  }
+  __syncthreads();
+  {
+    const int i = tid >> 3, c = tid & 7;            // element W[i][c] of my partial goes to slot `rank` of every CTA
+    const int it = i >> 3, ln = (i & 7) * 4 + (c >> 1), e = c & 1;
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { sr += Wp[w][it][ln][e]; si += Wp[w][it][ln][2 + e]; }
+    const cplx v = cmake(sr, si);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started
+#pragma unroll
+    for (int dst = 0; dst < LC_CL; ++dst) {
+      cplx* rs = cl.map_shared_rank(slots, dst);
+      rs[rank * 256 + tid] = v;
+    }
+  }
+  cl.sync();
+  {
+    cplx s0 = cadd(slots[tid], slots[256 + tid]), s1 = cadd(slots[2 * 256 + tid], slots[3 * 256 + tid]);
+    cplx s2 = cadd(slots[4 * 256 + tid], slots[5 * 256 + tid]), s3 = cadd(slots[6 * 256 + tid], slots[7 * 256 + tid]);
+    W1[tid >> 3][tid & 7] = cadd(cadd(s0, s1), cadd(s2, s3));
+  }
+  __syncthreads();
+  // ---- phase 2: W <- op(T) W, four independent accumulator chains
+  {
+    const int i = tid >> 3, c = tid & 7;
+    cplx acc[4] = {zero, zero, zero, zero};
+    if (conjT) {
+#pragma unroll
+      for (int k = 0; k < QR_NB; ++k) cfma_conj(acc[k & 3], Tsm[k][i], W1[k][c]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < QR_NB; ++k) cfma(acc[k & 3], Tsm[i][k], W1[k][c]);
+    }
+    W2[i][c] = cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3]));
+  }
+  __syncthreads();
+  // ---- phase 3: C -= V W on my rows (K = 32), operands already in registers
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int r = rbeg + 8 * warp + 64 * s2 + lo;
+    double dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0}, er[2] = {0.0, 0.0}, ei[2] = {0.0, 0.0};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const cplx b = W2[kk * 4 + lk][lo];
+      dmma884(dr[0], dr[1], a3[s2][kk].x, b.x);
+      dmma884(er[0], er[1], -a3[s2][kk].y, b.y);
+      dmma884(di[0], di[1], a3[s2][kk].x, b.y);
+      dmma884(ei[0], ei[1], a3[s2][kk].y, b.x);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = c0 + 2 * lk + e;
+      if (r < rend && col < ncols) C[(size_t)col * ldc + r] = cmake(cv[s2][e].x - (dr[e] + er[e]), cv[s2][e].y - (di[e] + ei[e]));
+    }
+  }
+  // no trailing cluster barrier: every remote store into this CTA's shared memory precedes the cl.sync() above
+}
+
 __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
   size_t tot = (size_t)n * n;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
@@ -898,6 +1085,7 @@ __global__ void set_identity_kernel(cplx* Q, int ldq, int n) {
 }
 
 long long* g_qr_prof = nullptr;
+int g_qr_prof_rank = 1;        // cluster rank whose thread 0 is stamped by the paired panel kernel's profile instantiation
 template <int NW, int T>
 static int launch_panel_t(cudaStream_t st, cplx* A, int lda, int m, int nb, cplx* tau, double* dabs, cplx* Tf, size_t smem) {
   static SmemMemo memo, memo_prof;
@@ -932,6 +1120,16 @@ int g_larfb_cluster_max_cols = 256;   // column count up to which the row-split 
 static int launch_larfb(cudaStream_t st, const cplx* V, int ldv, int m, const cplx* T, int conjT, cplx* C, int ldc,
                         int ncols, int vmode = 0) {
   if (ncols <= 0) return 0;
+  static const bool narrow_ok = getenv("DQMC_LARFB_NARROW") == nullptr || atoi(getenv("DQMC_LARFB_NARROW")) != 0;
+  if (narrow_ok && vmode == 1 && ncols <= 16 && m >= 64 && m <= 1024) {
+    static SmemMemo memo_n;
+    const size_t smem = sizeof(cplx) * LC_CL * 256;
+    if (ensure_dynamic_smem(larfb_narrow_kernel, memo_n, smem)) return -1;
+    larfb_narrow_kernel<<<((ncols + 7) / 8) * LC_CL, 256, smem, st>>>(V, ldv, m, T, conjT, C, ldc, ncols);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return 0;
+  }
   if (ncols <= g_larfb_cluster_max_cols && m >= 64) {
     static SmemMemo memo;
     const size_t smem = sizeof(cplx) * LC_CL * 256;
@@ -1019,11 +1217,12 @@ int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, 
 template <int T>
 static int launch_panel_paired_t(cudaStream_t st, cplx* A, int lda, cplx* V, int ldv, int m, int np, double* dabs, int dup,
                                  cplx* Tf, size_t smem) {
-  static SmemMemo memo;
+  static SmemMemo memo, memo_prof;
   size_t smem_lim = 0;
-  if (ensure_max_dynamic_smem(qr_panel_paired_kernel<T>, memo, &smem_lim)) return -1;
+  if (ensure_max_dynamic_smem(qr_panel_paired_kernel<T, false>, memo, &smem_lim) || ensure_max_dynamic_smem(qr_panel_paired_kernel<T, true>, memo_prof, &smem_lim)) return -1;
   if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "paired qr panel: m=%d too large", m); return -1; }
-  qr_panel_paired_kernel<T><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf);
+  if (g_qr_prof) qr_panel_paired_kernel<T, true><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, g_qr_prof, g_qr_prof_rank);
+  else qr_panel_paired_kernel<T, false><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, nullptr, 0);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;
