@@ -84,6 +84,7 @@ struct dqmc_ctx {
   // only while it is known to hold.  sym_model: every operator handed to dqmc_set_operator has it (checked on the host);
   // sym_G: the current G has it (true after every calculate_greens of a symmetric model, measured for caller-supplied G).
   bool sym_lu_opt, sym_greens_opt, sym_model, sym_G;
+  bool wrap_sym_opt;                // half-matrix wrap (DQMC_WRAP_SYM=0: off)
   bool paired_opt;                  // half-matrix stabilization (paired Householder QR) for symmetric models (DQMC_PAIRED=0: off)
   double* d_sym;                    // [2] scratch of sym_violation
   HostCSC csc[DQMC_OP_COUNT];
@@ -199,6 +200,7 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   { const char* e = getenv("DQMC_GREENS_SYM"); c->sym_greens_opt = e ? atoi(e) != 0 : true; }
   c->sym_model = false; c->sym_G = false;
   { const char* e = getenv("DQMC_PAIRED"); c->paired_opt = e ? atoi(e) != 0 : true; }
+  { const char* e = getenv("DQMC_WRAP_SYM"); c->wrap_sym_opt = e ? atoi(e) != 0 : true; }
   const size_t n = c->n, nn = n * n;
   TRY(c, dmalloc(c, &c->G, nn));
   TRY(c, dmalloc(c, &c->Gtmp, nn));
@@ -555,26 +557,30 @@ static void push_B(dqmc_ctx* c, Chain& ch, int op, int slice) {
 }
 static bool op_is_rows(int op) { return op == DQMC_B_RIGHT || op == DQMC_B_INV_RIGHT; }
 
-static int run_chain(dqmc_ctx* c, bool rows, cplx* mat, const Chain& ch, const double* colscale, double* colnorm2, int nvtot = 0) {
+static int run_chain(dqmc_ctx* c, bool rows, cplx* mat, const Chain& ch, const double* colscale, double* colnorm2, int nvtot = 0,
+                     int mirror = 0) {
   return launch_apply_chain(rows, mat, c->n, c->n, ch, c->hs, c->N, c->p.lambda * c->p.delta_tau, colscale, colnorm2,
-                            c->num_sms, c->st, nvtot);
+                            c->num_sms, c->st, nvtot, mirror);
 }
 
-static int apply_B(dqmc_ctx* c, int op, int slice, cplx* mat) {
+static int apply_B(dqmc_ctx* c, int op, int slice, cplx* mat, int mirror = 0) {
   Chain ch; ch.nsteps = 0;
   push_B(c, ch, op, slice);
-  return run_chain(c, op_is_rows(op), mat, ch, nullptr, nullptr);
+  return run_chain(c, op_is_rows(op), mat, ch, nullptr, nullptr, 0, mirror);
 }
 
 // wrap_greens! (stack.jl:316-325)
 static int wrap_greens_dev(dqmc_ctx* c, cplx* g, int slice, int dir) {
   ScopedTimer t(c, TM_WRAP);
+  // B, B^-1 and (while sym_G holds) G have the antiunitary flavour symmetry, hence B G and (B G) B^-1 too: each pass works on
+  // half of the vectors and writes the other half as their mirror image (DQMC_WRAP_SYM=0: full passes)
+  const int mir = (c->wrap_sym_opt && c->sym_model && c->sym_G && (g == c->G || g == c->Gtmp) && c->n % 2 == 0) ? 1 : 0;
   if (dir == -1) {
-    TRY(c, apply_B(c, DQMC_B_INV_LEFT, slice - 1, g));
-    TRY(c, apply_B(c, DQMC_B_RIGHT, slice - 1, g));
+    TRY(c, apply_B(c, DQMC_B_INV_LEFT, slice - 1, g, mir));
+    TRY(c, apply_B(c, DQMC_B_RIGHT, slice - 1, g, mir));
   } else {
-    TRY(c, apply_B(c, DQMC_B_LEFT, slice, g));
-    TRY(c, apply_B(c, DQMC_B_INV_RIGHT, slice, g));
+    TRY(c, apply_B(c, DQMC_B_LEFT, slice, g, mir));
+    TRY(c, apply_B(c, DQMC_B_INV_RIGHT, slice, g, mir));
   }
   return 0;
 }

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
                                                           Chain chain, const double* __restrict__ hsfield,
                                                           int nsites, double lam_dtau,
                                                           const double* __restrict__ colscale,
-                                                          double* __restrict__ colnorm2, int nvtot) {
+                                                          double* __restrict__ colnorm2, int nvtot, int mirror) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ldx = ROWS ? n + 1 : n;
   cplx* x = reinterpret_cast<cplx*>(smem_raw);
@@ -179,8 +179,21 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
     if (tid == 0) {
       for (int v = 0; v < nvec; ++v) bulk_s2g(mat + (size_t)(v0 + v) * ld, x + (size_t)v * ldx, (unsigned)(n * sizeof(cplx)));
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    if (mirror) {
+      // the matrix has the antiunitary flavour symmetry [[A, B], [-conj(B), conj(A)]] and only its left-half columns were
+      // processed: column c + n/2 is the partner (-conj(bottom half); conj(top half)) of column c
+      const int h = n >> 1;
+      for (int v = 0; v < nvec; ++v) {
+        const cplx* xv = x + (size_t)v * ldx;
+        cplx* dst = mat + (size_t)(v0 + v + h) * ld;
+        for (int j = tid; j < n; j += blockDim.x) {
+          const cplx t = xv[j < h ? j + h : j - h];
+          dst[j] = j < h ? cmake(-t.x, t.y) : cmake(t.x, -t.y);
+        }
+      }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (!ROWS) {
     for (int v = 0; v < nvec; ++v) {
       const double sc = colscale ? colscale[v0 + v] : 1.0;
@@ -204,17 +217,25 @@ __global__ void __launch_bounds__(256) apply_chain_kernel(cplx* __restrict__ mat
     }
   } else {
     const int tot = nvec * n;
+    const int h = n >> 1;
     for (int e = tid; e < tot; e += blockDim.x) {
       int v = e % nvec, j = e / nvec;
-      mat[(size_t)j * ld + v0 + v] = x[(size_t)v * ldx + j];
+      const cplx t = x[(size_t)v * ldx + j];
+      mat[(size_t)j * ld + v0 + v] = t;
+      // upper-half rows only were processed: row r + n/2 is (-conj(right half), conj(left half)) of row r
+      if (mirror) mat[(size_t)(j < h ? j + h : j - h) * ld + v0 + v + h] = j < h ? cmake(t.x, -t.y) : cmake(-t.x, t.y);
     }
   }
 }
 
 int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, const double* hsfield,
                        int nsites, double lam_dtau, const double* colscale, double* colnorm2,
-                       int num_sms, cudaStream_t stream, int nvtot) {
+                       int num_sms, cudaStream_t stream, int nvtot, int mirror) {
   if (nvtot <= 0 || nvtot > n) nvtot = n;
+  if (mirror) {
+    if (n % 2 != 0 || colscale != nullptr || colnorm2 != nullptr) { snprintf(g_errbuf, sizeof(g_errbuf), "apply_chain: mirror mode needs even n and a plain write-back"); return -1; }
+    nvtot = n / 2;
+  }
   const size_t smem_cap = 200 * 1024;
   const size_t tab_bytes = sizeof(double4) * (size_t)nsites;
   const int ldx = rows ? n + 1 : n;
@@ -238,9 +259,9 @@ int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, 
   if (ensure_max_dynamic_smem(apply_chain_kernel<false>, memo_cols, nullptr)) return -1;
   if (ensure_max_dynamic_smem(apply_chain_kernel<true>, memo_rows, nullptr)) return -1;
   if (rows)
-    apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot);
+    apply_chain_kernel<true><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot, mirror);
   else
-    apply_chain_kernel<false><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot);
+    apply_chain_kernel<false><<<grid, 256, smem, stream>>>(mat, n, ld, nvec, chain, hsfield, nsites, lam_dtau, colscale, colnorm2, nvtot, mirror);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;

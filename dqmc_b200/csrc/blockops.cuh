@@ -33,4 +33,6 @@ struct Chain {
 
 int launch_apply_chain(bool rows, cplx* mat, int n, int ld, const Chain& chain, const double* hsfield,
                        int nsites, double lam_dtau, const double* colscale, double* colnorm2,
-                       int num_sms, cudaStream_t stream, int nvtot = 0);   // nvtot: vectors to process (0 = all n)
+                       int num_sms, cudaStream_t stream, int nvtot = 0, int mirror = 0);
+// nvtot: vectors to process (0 = all n).  mirror: the matrix has the antiunitary flavour symmetry [[A, B], [-conj(B), conj(A)]]: only the
+// left-half columns (upper-half rows) are processed and the other half is written as their mirror image

@@ -1269,9 +1269,11 @@ int qr_factor_paired(cudaStream_t st, cplx* AL, int lda, int n, cplx* V, int ldv
       continue;
     }
     const int nnext = min(QP_NP, ntrail);
+    // the wide update of panel k needs V_k, T_k only and touches none of the next panel's columns: it may start as soon as the
+    // panel is factored, next to the narrow update below (which must see the wide update of panel k-1)
+    CUDA_TRY(cudaEventRecord(as->eA, st));
     if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, as->eB, 0));
     if (launch_larfb(st, Vp, ldv, m, T, 1, P + (size_t)np * lda, lda, nnext, 1)) return -1;
-    CUDA_TRY(cudaEventRecord(as->eA, st));
     CUDA_TRY(cudaStreamWaitEvent(as->st2, as->eA, 0));
     if (launch_larfb2(as->st2, Vp, ldv, m, T, 1, P + (size_t)(np + nnext) * lda, lda, ntrail - nnext, rhs ? rhs + r0 : nullptr, ldr,
                       rhs ? nrhs : 0, 1))

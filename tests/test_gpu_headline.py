@@ -146,12 +146,14 @@ np.savez({out!r}, G=mc.greens, h=mc.hsfield, nacc=nacc, consumed=consumed, ld=mc
 
 def test_symmetry_and_3m_switches_ab(tmp_path):
     # the default path (block-lookahead local updates, antiunitary-symmetric flush, half product in calculate_greens, 3M complex
-    # products) against (a) the plain one (DQMC_LU_SYM=0 DQMC_GREENS_SYM=0 DQMC_ZGEMM_3M=0) and (b) the per-site-lookahead
-    # local-update kernel (DQMC_LU_KERNEL=site) on a full up-down sweep at n = 576: same decisions, G to 1e-12
-    switches = ("DQMC_LU_SYM", "DQMC_GREENS_SYM", "DQMC_ZGEMM_3M", "DQMC_LU_KERNEL")
+    # products, half-matrix stabilization with the paired Householder QR) against (a) the plain one (DQMC_LU_SYM=0 DQMC_GREENS_SYM=0
+    # DQMC_ZGEMM_3M=0 DQMC_PAIRED=0: full matrices, sort-once unpaired QR), (b) the per-site-lookahead local-update kernel
+    # (DQMC_LU_KERNEL=site) and (c) full-matrix stabilization alone (DQMC_PAIRED=0) on a full up-down sweep at n = 576: same
+    # decisions, G to 1e-12
+    switches = ("DQMC_LU_SYM", "DQMC_GREENS_SYM", "DQMC_ZGEMM_3M", "DQMC_LU_KERNEL", "DQMC_PAIRED", "DQMC_LARFB_NARROW")
     res = {}
-    for tag, env in (("default", {}), ("plain", {"DQMC_LU_SYM": "0", "DQMC_GREENS_SYM": "0", "DQMC_ZGEMM_3M": "0"}),
-                     ("site_kernel", {"DQMC_LU_KERNEL": "site"})):
+    for tag, env in (("default", {}), ("plain", {"DQMC_LU_SYM": "0", "DQMC_GREENS_SYM": "0", "DQMC_ZGEMM_3M": "0", "DQMC_PAIRED": "0"}),
+                     ("site_kernel", {"DQMC_LU_KERNEL": "site"}), ("unpaired", {"DQMC_PAIRED": "0"})):
         out = str(tmp_path / f"{tag}.npz")
         e = dict(os.environ)
         for k in switches:
@@ -160,7 +162,7 @@ def test_symmetry_and_3m_switches_ab(tmp_path):
         subprocess.run([sys.executable, "-c", _AB_SCRIPT.format(root=ROOT, out=out)], check=True, env=e, timeout=900)
         res[tag] = dict(np.load(out))
     a = res["default"]
-    for tag in ("plain", "site_kernel"):
+    for tag in ("plain", "site_kernel", "unpaired"):
         b = res[tag]
         assert int(a["nacc"]) == int(b["nacc"]) and int(a["consumed"]) == int(b["consumed"]), tag
         assert np.array_equal(a["h"], b["h"]), tag
