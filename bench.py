@@ -449,9 +449,13 @@ def run_ours(args, cfg, rank, world, local_rank):
         n = mc.n
         acc_rate = nacc / (args.steps * M * N)
         f_sweep = acc_rate * M * N * 32.0 * n * n + (M // sm) * 107.3 * n ** 3
-        # what the device really executes per stabilization: UDT (QR 5.33 + Q^H 8 + T-product 8) + calculate_greens
-        # (2.5 GEMMs x 8 + QR 5.33 + Q^H on the rhs 8 + triangular solve 4) = 58.7 n^3  
-        f_sweep_own = acc_rate * M * N * 32.0 * n * n + (M // sm) * 58.7 * n ** 3
+        # what the device really executes per stabilization.  Full matrices: UDT (QR 5.33 + Q^H 8 + T-product 8)
+        # + calculate_greens (2.5 GEMMs x 8 + QR 5.33 + Q^H on the rhs 8 + triangular solve 4) = 58.7 n^3.  Half-matrix path (default
+        # for this model, n % 32 == 0): UDT (paired QR 2.67 + Q^H on n/2 columns 4 + half T-product 4) + calculate_greens (three half
+        # GEMMs 12 + paired QR 2.67 + Q^H on the n/2 right-hand sides 4 + triangular solve 2) = 31.3 n^3
+        paired = os.environ.get("DQMC_PAIRED", "1") != "0" and n % 32 == 0
+        c_own = 31.3 if paired else 58.7
+        f_sweep_own = acc_rate * M * N * 32.0 * n * n + (M // sm) * c_own * n ** 3
         b_sweep = M * 64.0 * n * n
         f64_peak = kr["fp64_peak_tflops"]
         t_roof = f_sweep / (f64_peak * 1e12) + b_sweep / (hbm_gbs * 1e9)
@@ -492,7 +496,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "sweep_roofline": {"flops": f_sweep, "bytes": b_sweep, "t_roofline_ms": t_roof * 1e3, "frac": t_roof / (t_dev / args.steps),
                                    "flops_note": "reference algorithm: 107.3 n^3 per stabilization (SURVEY 8d)",
                                    "flops_executed": f_sweep_own, "frac_executed": t_roof_own / (t_dev / args.steps),
-                                   "flops_executed_note": "what the device executes: 58.7 n^3 per stabilization (DESIGN.md 4)",
+                                   "flops_executed_note": "what the device executes: %.1f n^3 per stabilization (DESIGN.md 4; %s)" % (c_own, "half-matrix path, paired Householder QR" if paired else "full matrices"),
                                    "fp64_peak_tflops": f64_peak, "hbm_gbs": hbm_gbs},
                 "phases_ms_per_sweep": phases, "kernels": kr, "two_chains_per_gpu": two, "bfield_on": bfield,
                 "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",

@@ -1242,12 +1242,12 @@ extern "C" int dqmc_set_timing(dqmc_ctx* c, int32_t level) {
 // debug hook: per-phase cycle counters of the QR panel kernel (rank 0, thread 0), accumulated while enabled
 extern long long* g_qr_prof;
 extern int g_qr_prof_rank;
-extern "C" int dqmc_qr_profile(dqmc_ctx* c, int32_t enable, int64_t* out8) {
+extern "C" int dqmc_qr_profile(dqmc_ctx* c, int32_t enable, int64_t* out8 /* 16 values */) {
   if (enable > 0) g_qr_prof_rank = enable - 1;     // enable = 1 + cluster rank to stamp (paired panel kernel; the unpaired one stamps rank 0)
   CU(c, cudaSetDevice(c->p.device));
   CU(c, cudaStreamSynchronize(c->st));
-  if (out8) CU(c, cudaMemcpy(out8, c->d_prof + 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
-  CU(c, cudaMemset(c->d_prof + 8, 0, sizeof(long long) * 8));
+  if (out8) CU(c, cudaMemcpy(out8, c->d_prof + 8, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemset(c->d_prof + 8, 0, sizeof(long long) * 16));
   g_qr_prof = enable ? c->d_prof + 8 : nullptr;
   return 0;
 }

@@ -397,7 +397,7 @@ __device__ __forceinline__ void paired_t_columns(PairedSmem& S, int g, int lane,
 }
 
 template <int T, bool GENERAL, bool PROF>
-__device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
+__device__ __forceinline__ void panel_body_paired(PairedSmem& S, cg::cluster_group& cl, cplx* __restrict__ A, int lda,
                                                   cplx* __restrict__ Vout, int ldv, int m, int np, int r_begin, int nloc,
                                                   double* __restrict__ dabs_out, int dabs_dup, cplx* __restrict__ Tout,
                                                   long long* __restrict__ prof, int prof_rank) {
@@ -407,16 +407,22 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
   long long pcyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = PROF ? clock64() : 0;
   const bool stamp = PROF && prof != nullptr && (int)cl.block_rank() == prof_rank && threadIdx.x == 0;
 #define QSTAMP(k) do { if (PROF && stamp) { const long long t_ = clock64(); pcyc[k] += t_ - tprev; tprev = t_; } } while (0)
+  // sub-stamps of phase C (prof[8..12]); `dep` makes the stamp wait for the value it is meant to time
+  long long psub[5] = {0, 0, 0, 0, 0}, tsub = 0;
+#define QSUB(k, dep) do { if (PROF && stamp) { if ((dep) == 1.2345e-300) tsub++; const long long t_ = clock64(); psub[(k) - 8] += t_ - tsub; tsub = t_; } } while (0)
   constexpr bool KEEP = (T <= 10);               // current column kept in registers between the dot and the update phase
   const int rank = (int)cl.block_rank();
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
   const int col = lane & 15, comp = lane >> 4;
   const bool doT = (rank == panel_t_rank(m));
   cplx x[T];
+  {
+    const cplx* Ac = A + (size_t)col * lda + r_begin;
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int rl = 2 * (g + NW * t) + comp;
-    x[t] = rl < nloc ? a[rl * QR_LDA + col] : cmake(0.0, 0.0);
+    for (int t = 0; t < T; ++t) {
+      const int rl = 2 * (g + NW * t) + comp;
+      x[t] = (rl < nloc && col < np) ? Ac[rl] : cmake(0.0, 0.0);
+    }
   }
   if (col == 0) {
 #pragma unroll
@@ -478,6 +484,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
     QSTAMP(2);
     mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
     QSTAMP(3);
+    if (PROF) tsub = tprev;
     // ---- phase C: totals and reflector parameters.  Identical for every warp of the CTA, and the FP64 pipe is the bottleneck
     // when all eight evaluate the square roots and divisions at once (1160 cycles per step measured): warp 0 alone computes
     // them and broadcasts the per-column update coefficients through shared memory (~500 cycles).
@@ -488,6 +495,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
         const cplx c2 = cadd(S.xch[par][4][lane], S.xch[par][5][lane]), c3 = cadd(S.xch[par][6][lane], S.xch[par][7][lane]);
         tc = cadd(cadd(c0, c1), cadd(c2, c3));
       }
+      QSUB(8, tc.x);
       const double tj = __shfl_sync(0xffffffffu, tc.x, j);        // D1 of the current column = |x|^2 below row pair j
       const cplx tother = cmake(__shfl_xor_sync(0xffffffffu, tc.x, 16), __shfl_xor_sync(0xffffffffu, tc.y, 16));
       const cplx D1 = comp == 0 ? tc : tother, D2 = comp == 0 ? tother : tc;
@@ -495,6 +503,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
       const cplx ce0 = S.rowv[par][col], co0 = S.rowv[par][col + 16];
       const double q2 = cabs2(xe0) + cabs2(xo0);
       const double nrm2 = q2 + tj;
+      QSUB(9, nrm2 + ce0.x + D2.x);
       // The square roots and divisions of the reflector are the longest dependent chain of a step (sqrt, sqrt, 1/x, x/y one after
       // the other: ~1000 cycles measured).  Reciprocal square roots from the hardware approximation + two Newton steps (1-2 ulp,
       // no slow-path branches, the two chains interleave): |x| = nrm2 r, 1/|x| = r, |x_j| = q2 rq, |x|/|x_j| = |x| rq, and ONE
@@ -506,6 +515,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
       const double f = r * gi;                     // 1 / (|x| (|x| + |x_j|))
       const double rnj = r;                        // 1 / |x|
       const double tau = nx * gi;                  // |x| / (|x| + |x_j|)
+      QSUB(10, f);
       // products with row pair j that do not depend on the scale: t1 = x_j^H c_j, t2 = psi(x_j)^H c_j (in parallel with the chain above)
       cplx t1 = cmake(0.0, 0.0), t2 = t1;
       cfma_conj(t1, xe0, ce0); cfma_conj(t1, xo0, co0);
@@ -534,10 +544,12 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
         S.udiag[j] = cscale(ue0, rnj); S.udiag[j + 16] = cscale(uo0, rnj);
         S.sc4[0] = ue0; S.sc4[1] = uo0; S.sc4[2] = xe0; S.sc4[3] = xo0;
       }
+      QSUB(11, uc.x + pc.x);
     }
     __syncthreads();
     const cplx alpha = S.ab[0][lane], beta = S.ab[1][lane];
     tau_prev = S.tau_s[j];
+    QSUB(12, alpha.x);
     QSTAMP(4);
     // ---- phase D: c += A alpha + conj(B) beta on the rows below row pair j (A = my component of the current column,
     // B = the other one), alpha = -f uc, beta = +-f pc (e / o lanes); row pair j itself with u_j (rank 0)
@@ -569,40 +581,28 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
   if (doT) {
     paired_t_columns(S, g, lane, np - 1, tau_prev, S.gsm[(np - 1) & 1][0]);
   }
-  __syncthreads();   // udiag / T complete; the staging area is free (nobody reads `a` after the initial load)
-  // ---- R: rows at or above the quaternion diagonal keep their values, eliminated entries are exact zeros
+  __syncthreads();   // udiag / T complete
+  // ---- results straight from the registers: lanes c / c+16 hold the two rows of a quaternion row, i.e. every (column, row pair)
+  // is one aligned 32-byte sector.  R: rows at or above the quaternion diagonal keep their values, eliminated entries are exact
+  // zeros.  V = [v_0, psi(v_0), v_1, ...] explicit: column 2c = v_c, column 2c+1: rows (2q, 2q+1) = (-conj(v_o), conj(v_e)).
   const int q_begin = r_begin >> 1;              // global quaternion row of my first local one (within the panel)
+  if (col < np) {
+    cplx* Rc = A + (size_t)col * lda + r_begin;
+    cplx* V0 = Vout + (size_t)(2 * col) * ldv + r_begin;
+    cplx* V1 = V0 + ldv;
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int ql = g + NW * t, rl = 2 * ql + comp;
-    if (rl < nloc) a[rl * QR_LDA + col] = (q_begin + ql <= col) ? x[t] : cmake(0.0, 0.0);
-  }
-  __syncthreads();
-  for (int e = tid; e < nloc * QP_NP; e += NW * 32) {
-    const int rl = e % nloc, cc = e / nloc;
-    if (cc < np) A[(size_t)cc * lda + r_begin + rl] = a[rl * QR_LDA + cc];
-  }
-  __syncthreads();
-  // ---- V = [v_0, psi(v_0), v_1, ...] explicit: column 2c = v_c, column 2c+1: rows (2q, 2q+1) = (-conj(v_o), conj(v_e))
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int ql = g + NW * t, rl = 2 * ql + comp;
-    if (rl < nloc) {
-      const int qg = q_begin + ql;
-      cplx v = cmake(0.0, 0.0);
-      if (col < np) {
+    for (int t = 0; t < T; ++t) {
+      const int ql = g + NW * t, rl = 2 * ql + comp;
+      if (rl < nloc) {
+        const int qg = q_begin + ql;
+        Rc[rl] = (qg <= col) ? x[t] : cmake(0.0, 0.0);
+        cplx v = cmake(0.0, 0.0);
         if (qg > col) v = cscale(x[t], sc);
         else if (qg == col) v = S.udiag[col + 16 * comp];
+        V0[rl] = v;
+        V1[rl ^ 1] = comp == 0 ? cmake(v.x, -v.y) : cmake(-v.x, v.y);   // my value feeds the OTHER row of the pair in the partner column
       }
-      a[rl * QR_LDA + 2 * col] = v;
-      // my value feeds the OTHER row of the pair in the partner column
-      a[(rl ^ 1) * QR_LDA + 2 * col + 1] = comp == 0 ? cmake(v.x, -v.y) : cmake(-v.x, v.y);
     }
-  }
-  __syncthreads();
-  for (int e = tid; e < nloc * QR_NB; e += NW * 32) {
-    const int rl = e % nloc, cc = e / nloc;
-    Vout[(size_t)cc * ldv + r_begin + rl] = a[rl * QR_LDA + cc];
   }
   if (doT) {
     for (int e = tid; e < QR_NB * QR_NB; e += NW * 32) {
@@ -613,8 +613,9 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cplx* a, cg::cl
   }
   cl.sync();  // no CTA may exit while others may still write into its shared memory
   QSTAMP(6);
-  if (PROF && stamp) { for (int q = 0; q < 7; ++q) prof[q] += pcyc[q]; prof[7] += np; }
+  if (PROF && stamp) { for (int q = 0; q < 7; ++q) prof[q] += pcyc[q]; prof[7] += np; for (int q = 0; q < 5; ++q) prof[8 + q] += psub[q]; }
 #undef QSTAMP
+#undef QSUB
 }
 
 // Row split of the paired panel: rank 0 owns the first 32 interleaved rows (16 quaternion rows, the diagonal block), the rest
@@ -632,14 +633,8 @@ qr_panel_paired_kernel(cplx* __restrict__ A, int lda, cplx* __restrict__ Vout, i
   const int nloc = rank == 0 ? min(m, QR_NB) : max(0, min(m, r_begin + rs1) - r_begin);
   const int tid = threadIdx.x;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* a = reinterpret_cast<cplx*>(smem_raw);   // staging for the coalesced load / stores: a[rl*QR_LDA + c]
   __shared__ __align__(16) PairedSmem S;
 
-  for (int e = tid; e < nloc * QP_NP; e += 256) {
-    const int rl = e % nloc, cc = e / nloc;
-    a[rl * QR_LDA + cc] = cc < np ? A[(size_t)cc * lda + r_begin + rl] : cmake(0.0, 0.0);
-  }
   if (rank == panel_t_rank(m))
     for (int e = tid; e < QR_NB * (QR_NB + 1); e += 256) (&S.Tsm[0][0])[e] = cmake(0.0, 0.0);
   if (tid < QR_NB) S.udiag[tid] = cmake(0.0, 0.0);
@@ -649,8 +644,8 @@ qr_panel_paired_kernel(cplx* __restrict__ A, int lda, cplx* __restrict__ Vout, i
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (rank == 0) panel_body_paired<2, true, PROF>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
-  else panel_body_paired<T, false, PROF>(S, a, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
+  if (rank == 0) panel_body_paired<2, true, PROF>(S, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
+  else panel_body_paired<T, false, PROF>(S, cl, A, lda, Vout, ldv, m, np, r_begin, nloc, dabs_out, dabs_dup, Tout, prof, prof_rank);
 }
 
 // =====================================================================================================
@@ -1217,12 +1212,9 @@ int qr_form_q(cudaStream_t st, const cplx* A, int lda, int n, const cplx* tfac, 
 template <int T>
 static int launch_panel_paired_t(cudaStream_t st, cplx* A, int lda, cplx* V, int ldv, int m, int np, double* dabs, int dup,
                                  cplx* Tf, size_t smem) {
-  static SmemMemo memo, memo_prof;
-  size_t smem_lim = 0;
-  if (ensure_max_dynamic_smem(qr_panel_paired_kernel<T, false>, memo, &smem_lim) || ensure_max_dynamic_smem(qr_panel_paired_kernel<T, true>, memo_prof, &smem_lim)) return -1;
-  if (smem > smem_lim) { snprintf(g_errbuf, sizeof(g_errbuf), "paired qr panel: m=%d too large", m); return -1; }
-  if (g_qr_prof) qr_panel_paired_kernel<T, true><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, g_qr_prof, g_qr_prof_rank);
-  else qr_panel_paired_kernel<T, false><<<QR_CL, 256, smem, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, nullptr, 0);
+  (void)smem;   // the slab goes from global memory straight into registers and back: no staging area
+  if (g_qr_prof) qr_panel_paired_kernel<T, true><<<QR_CL, 256, 0, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, g_qr_prof, g_qr_prof_rank);
+  else qr_panel_paired_kernel<T, false><<<QR_CL, 256, 0, st>>>(A, lda, V, ldv, m, np, dabs, dup, Tf, nullptr, 0);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   return 0;

@@ -168,8 +168,9 @@ int dqmc_test_udt(dqmc_ctx* ctx, const double* x, double* U, double* D, double* 
  * [5] accepts, [8..15] per-warp stage-1 time, [16..23] per-warp role time before the speculative part,
  * [24..26] flush: first grid barrier, tiles, second grid barrier (debug; 32 values) */
 int dqmc_lu_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out32);
-/* per-phase cycle counters of the QR panel kernel accumulated since the last call (debug) */
-int dqmc_qr_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out8);
+/* per-phase cycle counters of the QR panel kernels accumulated since the last call (debug; out16: 16 values; enable = 1 + the
+ * cluster rank whose thread 0 is stamped in the paired kernel, 0 = off) */
+int dqmc_qr_profile(dqmc_ctx* ctx, int32_t enable, int64_t* out16);
 int64_t dqmc_kernel_launches(dqmc_ctx* ctx);   /* kernels launched by this context so far */
 
 #ifdef __cplusplus

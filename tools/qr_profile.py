@@ -8,7 +8,7 @@ L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 mc = DQMC(Params(L=L, slices=40, safe_mult=10, Bfield=False), device=0)
 rs = np.random.RandomState(0)
 mc.init(rs.rand(3, L * L, 40))
-out = np.zeros(8, dtype=np.int64)
+out = np.zeros(16, dtype=np.int64)
 mc.lib.dqmc_qr_profile(mc._ctx, 1, None)
 ms = mc.bench_kernel(3, 1)
 mc.lib.dqmc_qr_profile(mc._ctx, 0, out.ctypes.data_as(_l._I64))
