@@ -472,7 +472,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         if dom_map[dom] is not None:
             rf = dict(kr[dom_map[dom]])
             roof = {"kernel": dom_map[dom], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": rf["unit"],
-                    "frac": rf["frac"], "traffic": ncu_traffic({"wrap": "apply_chain_kernel", "udt": "qr_panel_kernel",
+                    "frac": rf["frac"], "traffic": ncu_traffic({"wrap": "apply_chain_kernel", "udt": "qr_panel_paired_kernel",
                                                                    "calculate_greens": "larfb_kernel"}[dom_map[dom]]),
                     "peak_source": rf["peak_source"]}
         else:
