@@ -335,7 +335,7 @@ struct PairedSmem {
   cplx xch[2][QR_CL][QR_NB];          // [parity][source CTA][slot]
   cplx rowv[2][QR_NB];                // [parity][slot]: row pair j (pushed by rank 0)
   cplx Tsm[QR_NB][QR_NB + 1];         // compact-WY T; rows {2g, 2g+1, 2g+16, 2g+17} belong to warp g
-  cplx gsm[2][2][QR_NB];              // [parity of the step][0]: V^H v_j, written by warp 0, read by all in the next step
+  cplx gsm[2][QR_NB];                 // [parity of the step]: V^H v_j, written by warp 0, read by all in the next step's exchange shadow
   cplx ab[2][QR_NB];                  // update coefficients alpha / beta of the step per lane (warp 0 -> all warps)
   cplx sc4[4];                        // u_j and x_j on row pair j (e, o)
   cplx udiag[QR_NB];                  // v_j on its own row pair: slot j = e, slot j+16 = o
@@ -479,15 +479,15 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cg::cluster_gro
     QSTAMP(1);
     if (doT && j > 0) {
       // the two T columns of the previous pair-step, in the shadow of the exchange
-      paired_t_columns(S, g, lane, j - 1, tau_prev, S.gsm[par ^ 1][0]);
+      paired_t_columns(S, g, lane, j - 1, tau_prev, S.gsm[par ^ 1]);
     }
     QSTAMP(2);
     mbar_wait_cluster(l_bar + 8 * par, (uint32_t)((j >> 1) & 1));
     QSTAMP(3);
     if (PROF) tsub = tprev;
-    // ---- phase C: totals and reflector parameters.  Identical for every warp of the CTA, and the FP64 pipe is the bottleneck
-    // when all eight evaluate the square roots and divisions at once (1160 cycles per step measured): warp 0 alone computes
-    // them and broadcasts the per-column update coefficients through shared memory (~500 cycles).
+    // ---- phase C: totals and reflector parameters.  Identical for every warp of the CTA: warp 0 alone computes them and
+    // broadcasts the per-column update coefficients through shared memory (a latency-bound dependent chain, ~800 cycles; eight
+    // warps evaluating it redundantly took as long and only added issue pressure).
     if (g == 0) {
       cplx tc;
       {
@@ -530,8 +530,8 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cg::cluster_gro
         // Gram entries against the finished columns (their dots and row entries arrived scaled by 1/|x_c|)
         const bool fin = col < j;
         const cplx z = cmake(0.0, 0.0);
-        S.gsm[par][0][2 * col] = fin ? cmake(rnj * uc.x, -rnj * uc.y) : z;        // v_c^H v_j        =  conj(uc)
-        S.gsm[par][0][2 * col + 1] = fin ? cmake(-rnj * pc.x, -rnj * pc.y) : z;   // psi(v_c)^H v_j   = -pc
+        S.gsm[par][2 * col] = fin ? cmake(rnj * uc.x, -rnj * uc.y) : z;        // v_c^H v_j        =  conj(uc)
+        S.gsm[par][2 * col + 1] = fin ? cmake(-rnj * pc.x, -rnj * pc.y) : z;   // psi(v_c)^H v_j   = -pc
         // (the entries against psi(v_j), conj(pc) and uc, are not needed: column 2j+1 of T follows from column 2j)
       }
       // update coefficients of my column: alpha = -f uc, beta = +-f pc (e / o lanes), zero for the finished columns
@@ -579,7 +579,7 @@ __device__ __forceinline__ void panel_body_paired(PairedSmem& S, cg::cluster_gro
     QSTAMP(5);
   }
   if (doT) {
-    paired_t_columns(S, g, lane, np - 1, tau_prev, S.gsm[(np - 1) & 1][0]);
+    paired_t_columns(S, g, lane, np - 1, tau_prev, S.gsm[(np - 1) & 1]);
   }
   __syncthreads();   // udiag / T complete
   // ---- results straight from the registers: lanes c / c+16 hold the two rows of a quaternion row, i.e. every (column, row pair)
