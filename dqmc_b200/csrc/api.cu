@@ -588,7 +588,9 @@ static int wrap_greens_dev(dqmc_ctx* c, cplx* g, int slice, int dir, bool treat_
 // ---------------------------------------------------------------------------------------------- UDT / greens
 // decompose_udt! (linalg.jl:20-39): X (in c->W[0], destroyed; column norms^2 in c->colnorm) -> U, D, T(W[2]).
 // Pivoting = one stable sort of the columns by norm, then unpivoted blocked Householder QR.
-static bool use_paired(const dqmc_ctx* c) { return c->paired_opt && c->sym_model && c->n % 32 == 0 && c->n >= 64; }
+// (the stack must come from the paired UDT too: its D is exactly paired, D[i] = D[i + n/2], which the half-matrix calculate_greens relies on;
+// the column-pivoted UDTs of DQMC_UDT=qrcp order their columns differently)
+static bool use_paired(const dqmc_ctx* c) { return c->paired_opt && c->sym_model && !c->udt_qrcp_sweep && c->n % 32 == 0 && c->n >= 64; }
 
 // The same for a matrix with the antiunitary flavour symmetry (every matrix of the stabilization path of a symmetric model):
 // only the left-half columns are sorted and factored, by PAIRED Householder steps (qr.cu), n/2 sequential steps instead of n and
