@@ -16,6 +16,9 @@ Conventions (they differ from quaternion_qr_blocked.py only by signs / normalisa
   give for free:   v_c^H v_j = r_c r_j conj(uc_c),  psi(v_c)^H v_j = -r_c r_j pc_c,  v_c^H psi(v_j) = r_c r_j conj(pc_c),
   psi(v_c)^H psi(v_j) = r_c r_j uc_c   (uc_c = u_j^H [column c],  pc_c = psi(u_j)^H [column c],  r = 1/|x|).
 
+The kernel evaluates |x|, 1/|x|, |x_j| and 1/(|x| + |x_j|) with reciprocal square roots / reciprocals refined by two Newton steps
+(1-2 ulp) instead of sqrt and divisions; the algebra below is the same, the results agree to rounding (tests/test_gpu_paired.py).
+
     python -m oracle.experiments.paired_panel_spec
 """
 import numpy as np
