@@ -1,5 +1,5 @@
 """Test infrastructure (oracle side): executable specification of the DEVICE paired-Householder panel kernel
-(`dqmc_b200/csrc/qr_paired.cu`), formula by formula, in the conventions the CUDA code uses.  Not used by the product.
+(`qr_panel_paired_kernel` in `dqmc_b200/csrc/qr.cu`), formula by formula, in the conventions the CUDA code uses.  Not used by the product.
 
 Conventions (they differ from quaternion_qr_blocked.py only by signs / normalisation):
 
