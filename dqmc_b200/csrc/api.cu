@@ -190,8 +190,17 @@ extern "C" int dqmc_create(dqmc_ctx** out, const dqmc_params* p) {
   cudaDeviceProp prop;
   CU(c, cudaGetDeviceProperties(&prop, p->device));
   c->num_sms = prop.multiProcessorCount;
-  CU(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  CU(c, cudaStreamCreateWithFlags(&c->qra.st2, cudaStreamNonBlocking));
+  // The main stream carries the latency-bound critical path (panel chain, narrow updates), the second one the wide trailing updates
+  // that run in its shadow: when both have a kernel ready, the critical path's CTAs must get the free SMs first (a cluster of 8 needs
+  // them within one GPC, which a 126-CTA wide update would otherwise occupy).  DQMC_STREAM_PRIO=0: equal priorities.
+  {
+    int prio_lo = 0, prio_hi = 0;
+    CU(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
+    const char* e = getenv("DQMC_STREAM_PRIO");
+    const bool prio = e ? atoi(e) != 0 : true;
+    CU(c, cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio ? prio_hi : 0));
+    CU(c, cudaStreamCreateWithPriority(&c->qra.st2, cudaStreamNonBlocking, prio ? prio_lo : 0));
+  }
   CU(c, cudaEventCreateWithFlags(&c->qra.eA, cudaEventDisableTiming));
   CU(c, cudaEventCreateWithFlags(&c->qra.eB, cudaEventDisableTiming));
   c->lookahead = getenv("DQMC_NO_LOOKAHEAD") == nullptr;
